@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- MLUPS of the fluctuating binary D3Q19 step on N B200s (weak scaling), with roofline and CPU baseline.
+
+Contract (one JSON line on stdout from rank 0):
+  metric   "MLUPS (fp64 binary fluct D3Q19)"  -- BASELINE.json's metric
+  value    whole-job million lattice-cell updates per second, state resident in HBM, CUDA-event timed,
+           max over ranks
+  e2e      same metric through the C ABI with HOST buffers: one output interval of the reference driver
+           (plot_int = 200 steps, main_run_job.cpp:90): restart upload of fold/gold (LBM_init) from pinned
+           host memory -> steps -> download of the 9 hydrovsbar fields (what WriteOutput writes)
+  roofline dominant kernel (fused collide+stream+density-scatter) against the MEASURED HBM copy bandwidth
+           (MEASURED_PEAKS.json), algorithmic bytes = 608 B per cell update
+  cpu_baseline  the reference's own LBM_timestep (oracle/_ref, OpenMP over the shim loops) or the C port,
+           timed on this host on a bounded sample
+
+`--impl reference` times the reference's CPU implementation alone (rank 0 only).
+A "step" is one LBM_timestep of the whole lattice.  Workload at every N: 512^3 cells per GPU (config 5 of
+BASELINE.json, weak scaling; slabs stacked along z), mixture rho = phi = 1 with kBT = 1e-5, alpha0 = 1.5.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MLUPS (fp64 binary fluct D3Q19)"
+UNIT = "MLUPS"
+BYTES_PER_CELL = 608  # 2 species x 19 populations x (1 read + 1 write) x 8 B
+PARAMS = dict(kBT=1e-5, tau_f=0.5, tau_g=0.5, alpha0=1.5, alpha1=0.0, kappa=4.0, rho_lo=0.0, rho_hi=1.0, seed=12345)
+E2E_STEPS = 200  # reference plot_int, main_run_job.cpp:90
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=512)
+    ap.add_argument("--ny", type=int, default=512)
+    ap.add_argument("--nz", type=int, default=512, help="planes PER GPU (weak scaling)")
+    ap.add_argument("--algo", default="fused", choices=["fused", "twopass"])
+    ap.add_argument("--kbt", type=float, default=PARAMS["kBT"])
+    ap.add_argument("--brick-lz", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=E2E_STEPS)
+    ap.add_argument("--cpu-size", type=int, default=64)
+    ap.add_argument("--cpu-steps", type=int, default=0, help="0 = sized for ~10-20 s")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); power.append(float(p[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------- CPU baseline
+def cpu_reference_run(size, steps, kbt):
+    """Times the reference's LBM_timestep on the host.  Returns dict for the `cpu_baseline` key."""
+    from oracle import oracle as om
+    om.build()
+    nthreads = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(nthreads))
+    if om.RefOracle.available(fast=True):
+        O = om.RefOracle(size, size, size, fast=True)
+        O.set_params(kBT=kbt, tau_f=PARAMS["tau_f"], tau_g=PARAMS["tau_g"], alpha0=PARAMS["alpha0"], alpha1=0.0, kappa=PARAMS["kappa"])
+        O.set_rng(2, 12345)  # per-thread mt19937 + std::normal_distribution behind amrex::RandomNormal
+        kind, cores = "reference", O.num_threads()
+    else:
+        O = om.PortOracle(size, size, size, fast=True)
+        O.set_params(kBT=kbt, tau_f=PARAMS["tau_f"], tau_g=PARAMS["tau_g"], alpha0=PARAMS["alpha0"], alpha1=0.0, kappa=PARAMS["kappa"],
+                     rho_lo=0.0, rho_hi=1.0)
+        kind, cores = "port", nthreads
+    O.init_mixture()
+    O.step(1)  # warm-up (page faults)
+    if steps <= 0:
+        t0 = time.perf_counter()
+        O.step(1)
+        dt = time.perf_counter() - t0
+        steps = int(max(2, min(400, 12.0 / max(dt, 1e-4))))
+    t0 = time.perf_counter()
+    O.step(steps)
+    dt = time.perf_counter() - t0
+    mlups = size ** 3 * steps / dt / 1e6
+    return {"value": mlups, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"mixture {size}^3, kBT={kbt:g}, {steps} steps of LBM_timestep in {dt:.1f} s "
+                      f"({'reference headers over oracle/shim, -O3 -march=x86-64-v3, OpenMP' if kind == 'reference' else 'C port, -O3, OpenMP'})"}, dt / steps
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res, sec_per_step = cpu_reference_run(a.cpu_size, 0, a.kbt)
+    # K timed "steps", each a bounded sample: one LBM_timestep of the cpu_size^3 sample box
+    from oracle import oracle as om
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"mixture rho=phi=1, kBT={a.kbt:g}, alpha0={PARAMS['alpha0']}, tau=1/2; bounded sample {a.cpu_size}^3 of the "
+                               f"{a.nx}x{a.ny}x{a.nz * a.gpus} job", "sample_cells": a.cpu_size ** 3},
+        "cpu_baseline": res,
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_b200(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import bflbm_b200 as b
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the b200 arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nzl = a.nz
+    nz_global = nzl * world
+    prm = b.Params(**{**PARAMS, "kBT": a.kbt})
+    stream = torch.cuda.Stream()  # a real (non-default) stream: the library launches on it and the events are recorded on it
+    torch.cuda.set_stream(stream)
+
+    if world == 1:
+        lat = b.Lattice(a.nx, a.ny, nzl, params=prm, device=local)
+        stepper = lat
+    else:
+        from bflbm_b200.distributed import SlabLattice
+        stepper = SlabLattice(a.nx, a.ny, nz_global, params=prm, device=local)
+        lat = stepper.lat
+    lat.set_stream(stream.cuda_stream)
+    lat.set_algorithm(a.algo)
+    if a.brick_lz:
+        lat.set_tiling(a.brick_lz)
+    stepper.init_mixture()
+    cells_local = a.nx * a.ny * nzl
+    cells = cells_local * world
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- timed region: W warm-up steps, then exactly K steps, CUDA events on the launching stream -------
+    stepper.step(a.warmup)
+    barrier()
+    launches0 = lat.kernel_launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    stepper.step(a.steps)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = lat.kernel_launches - launches0
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    value = cells * a.steps / (ms * 1e-3) / 1e6
+    nan_count = 0
+    try:
+        nan_count = lat.check_nan()
+    except b.BflbmError:
+        nan_count = -1
+
+    # ---- dominant kernel alone: per-kernel events inside the library, same step count -------------------
+    roofline = None
+    peak, peak_src = measured_peak()
+    lat.set_profiling(True)
+    stepper.step(a.steps)
+    lat.sync()
+    per_kernel, nprof = lat.profile()
+    lat.set_profiling(False)
+    if nprof > 0 and per_kernel[0] > 0:
+        achieved = BYTES_PER_CELL * cells_local / (per_kernel[0] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "kernel": "k_step_fused" if a.algo == "fused" else "k_step_twopass",
+                    "kernel_ms": per_kernel[0], "other_kernels_ms": {"fold_or_wrap": per_kernel[1], "pack_or_density": per_kernel[2],
+                                                                     "unpack_or_wrap": per_kernel[3]},
+                    "algorithmic_bytes_per_cell": BYTES_PER_CELL,
+                    "step_frac_of_roofline": (BYTES_PER_CELL * cells_local / (ms / a.steps * 1e-3) / 1e9) / peak}
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr):
+            try:
+                roofline["traffic"] = json.load(open(tr)).get("bytes_per_launch")
+            except Exception:
+                pass
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        e2e = run_e2e(a, b, np, torch, lat, stepper, world, cells, cells_local)
+
+    cpu = None
+    if rank == 0 and not a.no_cpu and world == 1:
+        cpu, _ = cpu_reference_run(a.cpu_size, a.cpu_steps, a.kbt)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"weak-scaling {a.nx}x{a.ny}x{nzl} cells per GPU ({a.nx}x{a.ny}x{nz_global} total), fluctuating binary "
+                                   f"D3Q19 mixture rho=phi=1, kBT={a.kbt:g}, alpha0={PARAMS['alpha0']}, tau_f=tau_g=1/2 (BASELINE.json configs[4])",
+                       "cells_per_gpu": cells_local, "algorithm": a.algo, "parallelism": f"z-slabs x{world}",
+                       "l2": "working set (two lattices, %.1f GB per GPU) far exceeds the 126 MB L2; no flush needed" % (lat.device_bytes / 1e9),
+                       "nonfinite_after_run": nan_count},
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(a, b, np, torch, lat, stepper, world, cells, cells_local):
+    """One output interval of the reference driver through the public API with host buffers."""
+    import torch.distributed as dist
+    nsteps = a.e2e_steps
+    shape = (19, lat.nz, lat.ny, lat.nx)
+    try:
+        if world == 1:
+            f = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+            g = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+        out = torch.empty((9, lat.nz, lat.ny, lat.nx), dtype=torch.float64, pin_memory=True)
+        pinned = True
+    except Exception:
+        pinned = False
+        f = torch.empty(shape, dtype=torch.float64)
+        g = torch.empty(shape, dtype=torch.float64)
+        out = torch.empty((9, lat.nz, lat.ny, lat.nx), dtype=torch.float64)
+    if world > 1:
+        return stepper.run_e2e(nsteps, out, pinned)
+    fn, gn = f.numpy(), g.numpy()
+    lib = lat.lib
+    from bflbm_b200.lattice import _check
+    _check(lib.bflbm_get_populations(lat.h, fn.ctypes.data, gn.ctypes.data))  # untimed: makes the host checkpoint
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _check(lib.bflbm_init_from_populations(lat.h, fn.ctypes.data, gn.ctypes.data))
+    _check(lib.bflbm_step(lat.h, nsteps))
+    _check(lib.bflbm_get_hydrovars_bar(lat.h, out.numpy().ctypes.data))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    mass = float(out[0].sum())
+    return {"value": cells * nsteps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * 19 * 8 * cells_local / nsteps,
+            "d2h_bytes_per_step": 9 * 8 * cells_local / nsteps, "steps_per_interval": nsteps, "seconds": dt, "pinned_host": pinned,
+            "what": "bflbm_init_from_populations(host f,g) + bflbm_step(200) + bflbm_get_hydrovars_bar(host), wall clock",
+            "result_mass_rho": mass}
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200(args)

@@ -1,0 +1,337 @@
+// CUDA kernels of the fluctuating binary D3Q19 step (sm_100a).
+//
+// Data layout in HBM (one z-slab of the periodic box; the whole box is the slab with nzl = nz):
+//   X  : double [2 species][19][nzl+2][ny][nx]   "pre-stream" populations: the post-stream population
+//        f_i(x) of the reference's fold/gold equals X_i(x - c_i) (pull).  Plane 0 and nzl+1 are ghost
+//        planes (neighbour slab or periodic image); x and y wrap by index arithmetic.
+//   R  : double2 [nzl+2][ny][nx]                  (rho, phi) of the post-stream populations, with ghost planes
+//   E  : double2 [brick][Lz+2][Ty+2][Tx+2]        per-brick partial sums of next-step (rho, phi) (fused algorithm)
+// SoA per component = AMReX's own FAB order (x fastest ... component slowest).
+#pragma once
+#include "physics.cuh"
+
+namespace bflbm {
+
+struct Geom {
+  int nx, ny, nzl;      // local slab (valid cells)
+  int nz_global, z0;    // global box height and first global plane of the slab
+  long long plane;      // nx*ny
+  long long comp;       // (nzl+2)*plane  : stride between components of X
+};
+
+__device__ __forceinline__ long long cell_global(const Geom& G, int x, int y, int zl) {
+  return (long long)x + (long long)G.nx * ((long long)y + (long long)G.ny * (long long)(G.z0 + zl));
+}
+
+// Neighbour index tables of one cell: xs[c+1] = wrapped x + c, yrow[c+1] = (wrapped y + c)*nx,
+// zpl[c+1] = (zl + 1 + c)*plane (ghost planes make z wrap-free).
+struct CellIdx {
+  int xs[3];
+  long long yrow[3], zpl[3];
+};
+__device__ __forceinline__ CellIdx cell_idx(const Geom& G, int x, int y, int zl) {
+  CellIdx I;
+  I.xs[0] = (x == 0) ? G.nx - 1 : x - 1;
+  I.xs[1] = x;
+  I.xs[2] = (x == G.nx - 1) ? 0 : x + 1;
+  I.yrow[0] = (long long)((y == 0) ? G.ny - 1 : y - 1) * G.nx;
+  I.yrow[1] = (long long)y * G.nx;
+  I.yrow[2] = (long long)((y == G.ny - 1) ? 0 : y + 1) * G.nx;
+  I.zpl[0] = (long long)zl * G.plane;
+  I.zpl[1] = (long long)(zl + 1) * G.plane;
+  I.zpl[2] = (long long)(zl + 2) * G.plane;
+  return I;
+}
+// index of the cell at (x,y,z) + s*c_i, s = +1 or -1
+template <int S>
+__device__ __forceinline__ long long nbr(const CellIdx& I, int i) {
+  return I.zpl[1 + S * cz(i)] + I.yrow[1 + S * cy(i)] + I.xs[1 + S * cx(i)];
+}
+
+// pull the 19 post-stream populations of one species: f_i(x) = X_i(x - c_i)
+__device__ __forceinline__ void pull19(const double* __restrict__ Xs, const Geom& G, const CellIdx& I, double (&f)[Q]) {
+#pragma unroll
+  for (int i = 0; i < Q; ++i) f[i] = __ldg(Xs + (long long)i * G.comp + nbr<-1>(I, i));
+}
+
+// ---------------------------------------------------------------------------------------------
+// two-pass algorithm, pass 1: (rho, phi) of the post-stream populations
+// (LBM_hydrovars_density, LBM_binary.H:343-354: sequential sum i = 0..18)
+__global__ void __launch_bounds__(256) k_density(Geom G, const double* __restrict__ X, double2* __restrict__ R) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zl = blockIdx.z;
+  if (x >= G.nx || y >= G.ny) return;
+  const CellIdx I = cell_idx(G, x, y, zl);
+  double f[Q], g[Q];
+  pull19(X, G, I, f);
+  pull19(X + (long long)Q * G.comp, G, I, g);
+  double rho = 0., phi = 0.;
+#pragma unroll
+  for (int i = 0; i < Q; ++i) { rho += f[i]; phi += g[i]; }
+  R[I.zpl[1] + I.yrow[1] + x] = make_double2(rho, phi);
+}
+
+// gradients of rho and phi from the density field (LBM_binary.H:134-150)
+__device__ __forceinline__ void density_gradients(const double2* __restrict__ R, const CellIdx& I, double (&grho)[3], double (&gphi)[3]) {
+  double nr[Q], np[Q];
+  nr[0] = np[0] = 0.;
+#pragma unroll
+  for (int i = 1; i < Q; ++i) {
+    const double2 v = __ldg(R + nbr<+1>(I, i));
+    nr[i] = v.x;
+    np[i] = v.y;
+  }
+  gradient19(nr, grho);
+  gradient19(np, gphi);
+}
+
+// two-pass algorithm, pass 2: pull-stream + hydro + collide (+noise) + store.
+// Covers K1 (collide_stream, LBM_binary.H:565-573), K4 (thermal_noise :91-128) and K5 (hydrovars :309-311)
+// of SURVEY.md 2b in one kernel; the reference's two Swaps (:579-580) become a pointer swap on the host.
+template <bool NOISE>
+__global__ void __launch_bounds__(256) k_step_twopass(Geom G, DevParams P, long long step, const double* __restrict__ X,
+                                                       double* __restrict__ Xn, const double2* __restrict__ R) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zl = blockIdx.z;
+  if (x >= G.nx || y >= G.ny) return;
+  const CellIdx I = cell_idx(G, x, y, zl);
+  double mf[Q], mg[Q];
+  {
+    double f[Q];
+    pull19(X, G, I, f);
+    moments(f, mf);
+    pull19(X + (long long)Q * G.comp, G, I, f);
+    moments(f, mg);
+  }
+  double grho[3], gphi[3];
+  density_gradients(R, I, grho, gphi);
+  const NoiseKey nk = make_noise_key(P.seed, (unsigned long long)cell_global(G, x, y, zl), step);
+  collide_cell<NOISE>(P, grho, gphi, nk, mf, mg);
+  const long long c = I.zpl[1] + I.yrow[1] + x;
+  double f[Q];
+  populations(mf, f);
+#pragma unroll
+  for (int i = 0; i < Q; ++i) Xn[(long long)i * G.comp + c] = f[i];
+  populations(mg, f);
+#pragma unroll
+  for (int i = 0; i < Q; ++i) Xn[(long long)(Q + i) * G.comp + c] = f[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// plane copies (ghost-plane wrap of a whole-box lattice, halo pack/unpack of a slab)
+struct CopyList {
+  int n;
+  long long src[44], dst[44];  // offsets in doubles
+};
+__global__ void k_copy_planes(CopyList L, const double* __restrict__ src, double* __restrict__ dst, long long count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int j = blockIdx.y;
+  dst[L.dst[j] + i] = src[L.src[j] + i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// initial conditions.  X_i(x) = w_i * dens(x + c_i), so that the pulled populations are w_i * dens(x)
+// like the reference's f(x,y,z,i) = w[i]*rho.
+// mode 0 mixture (LBM_binary.H:606-618), 1 stripe (:672-686), 2 droplet (:709-737)
+struct InitSpec {
+  int mode;
+  double rho_lo, rho_hi, kappa, frac, radius;
+};
+__device__ __forceinline__ void init_density(const InitSpec& S, const Geom& G, int x, int y, int zg, double& rho, double& phi) {
+  if (S.mode == 0) {
+    rho = 2. * 0.5;
+    phi = 2. * 0.5;
+  } else if (S.mode == 1) {
+    const double pos_lo = (-0.5 * S.frac) * G.nz_global, pos_hi = (0.5 * S.frac) * G.nz_global;
+    const double pos = (double)(zg - G.nz_global / 2);  // integer division, LBM_binary.H:680
+    const double sk = sqrt(S.kappa);
+    rho = (S.rho_hi - S.rho_lo) * 0.5 * (tanh((pos - pos_lo) / sk) + tanh((pos_hi - pos) / sk)) + S.rho_lo;
+    phi = (S.rho_hi + S.rho_lo) - rho;
+  } else {
+    const double Rr = S.radius * G.nx;
+    const double rx = x - G.nx / 2., ry = y - G.ny / 2.;
+    const double rz = (double)(zg - G.nx / 2);  // box[0] and integer division, LBM_binary.H:725
+    const double r = sqrt(rx * rx + ry * ry + rz * rz);
+    rho = (S.rho_hi - S.rho_lo) * (1. + tanh((Rr - r) / sqrt(S.kappa))) / 2. + S.rho_lo;
+    phi = (S.rho_hi + S.rho_lo) - rho;
+  }
+}
+// fills planes zl = -1 .. nzl (ghost planes included: no exchange needed after an analytic init)
+__global__ void __launch_bounds__(256) k_init(Geom G, InitSpec S, double* __restrict__ X, double2* __restrict__ R) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zl = (int)blockIdx.z - 1;
+  if (x >= G.nx || y >= G.ny) return;
+  const long long c = (long long)(zl + 1) * G.plane + (long long)y * G.nx + x;
+  const int nzg = G.nz_global;
+#pragma unroll
+  for (int i = 0; i < Q; ++i) {
+    int xx = x + cx(i), yy = y + cy(i), zz = G.z0 + zl + cz(i);
+    xx = xx < 0 ? xx + G.nx : (xx >= G.nx ? xx - G.nx : xx);
+    yy = yy < 0 ? yy + G.ny : (yy >= G.ny ? yy - G.ny : yy);
+    zz = ((zz % nzg) + nzg) % nzg;
+    double rho, phi;
+    init_density(S, G, xx, yy, zz, rho, phi);
+    X[(long long)i * G.comp + c] = wq(i) * rho;
+    X[(long long)(Q + i) * G.comp + c] = wq(i) * phi;
+  }
+  // densities of the pulled populations, reference order (sum_i w_i * dens)
+  {
+    const int zg = (((G.z0 + zl) % nzg) + nzg) % nzg;
+    double rho, phi, sr = 0., sp = 0.;
+    init_density(S, G, x, y, zg, rho, phi);
+#pragma unroll
+    for (int i = 0; i < Q; ++i) { sr += wq(i) * rho; sp += wq(i) * phi; }
+    R[c] = make_double2(sr, sp);
+  }
+}
+
+// restart: staging holds post-stream populations f_i(x) for planes zl = zlo-1 .. zhi (one ghost plane on
+// each side of the chunk), component-major [38][np][ny][nx]; writes X_i(x) = f_i(x + c_i) for zl in [zlo, zhi).
+__global__ void __launch_bounds__(256) k_scatter_populations(Geom G, int zlo, int np, const double* __restrict__ stage,
+                                                              double* __restrict__ X) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zl = zlo + (int)blockIdx.z;
+  if (x >= G.nx || y >= G.ny) return;
+  const CellIdx I = cell_idx(G, x, y, zl);
+  const long long c = I.zpl[1] + I.yrow[1] + x;
+  const long long scomp = (long long)np * G.plane;
+#pragma unroll
+  for (int i = 0; i < Q; ++i) {
+    // source plane index inside the stage: (zl + cz) - (zlo - 1)
+    const long long s = (long long)(zl + cz(i) - zlo + 1) * G.plane + I.yrow[1 + cy(i)] + I.xs[1 + cx(i)];
+    X[(long long)i * G.comp + c] = stage[(long long)i * scomp + s];
+    X[(long long)(Q + i) * G.comp + c] = stage[(long long)(Q + i) * scomp + s];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// observers: everything the reference keeps in hydrovs / hydrovsbar / fnoisevs / gnoisevs / fold / gold is
+// recomputed on demand from (X, R) for planes [zlo, zlo + gridDim.z).  out is component-major over the chunk.
+enum ObserveMode { OBS_POP = 0, OBS_HYDRO = 1, OBS_HBAR = 2, OBS_NOISE = 3, OBS_NORMALS = 4 };
+
+template <int MODE, bool NOISE>
+__global__ void __launch_bounds__(256) k_observe(Geom G, DevParams P, long long step, int zlo, const double* __restrict__ X,
+                                                  const double2* __restrict__ R, double* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zc = blockIdx.z, zl = zlo + zc;
+  if (x >= G.nx || y >= G.ny) return;
+  const CellIdx I = cell_idx(G, x, y, zl);
+  const long long oc = (long long)gridDim.z * G.plane;                       // component stride of the chunk
+  const long long o = (long long)zc * G.plane + (long long)y * G.nx + x;    // cell offset in the chunk
+  const NoiseKey nk = make_noise_key(P.seed, (unsigned long long)cell_global(G, x, y, zl), step);
+  if (MODE == OBS_NORMALS) {
+    float n[36];
+    cell_normals(nk, n);
+#pragma unroll
+    for (int d = 0; d < 33; ++d) out[o * 33 + d] = (double)n[d];
+    return;
+  }
+  double f[Q], g[Q];
+  pull19(X, G, I, f);
+  pull19(X + (long long)Q * G.comp, G, I, g);
+  if (MODE == OBS_POP) {
+#pragma unroll
+    for (int i = 0; i < Q; ++i) { out[(long long)i * oc + o] = f[i]; out[(long long)(Q + i) * oc + o] = g[i]; }
+    return;
+  }
+  double mf[Q], mg[Q];
+  moments(f, mf);
+  moments(g, mg);
+  // rho, phi as the reference's hydrovars_bar_density: sequential sums (LBM_binary.H:322-330)
+  double rho = 0., phi = 0.;
+#pragma unroll
+  for (int i = 0; i < Q; ++i) { rho += f[i]; phi += g[i]; }
+  if (MODE == OBS_HBAR) {
+    const bool hf = fabs(mf[0]) > (double)FLT_EPSILON, hg = fabs(mg[0]) > (double)FLT_EPSILON;
+    out[0 * oc + o] = rho;
+    out[1 * oc + o] = phi;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      out[(2 + k) * oc + o] = hf ? mf[1 + k] / mf[0] : 0.;
+      out[(6 + k) * oc + o] = hg ? mg[1 + k] / mg[0] : 0.;
+    }
+    out[5 * oc + o] = mf[0] + mg[0];
+    return;
+  }
+  float n[36];
+  if (NOISE) cell_normals(nk, n);
+  else {
+#pragma unroll
+    for (int d = 0; d < 36; ++d) n[d] = 0.f;
+  }
+  if (MODE == OBS_NOISE) {
+    // fnoisevs / gnoisevs (LBM_binary.H:113-127)
+    const double aj = NOISE ? sqrt(P.amp_j * fabs(rho * phi / (rho + phi))) : 0.;
+    const double sf = NOISE ? sqrt(P.amp_s * fabs(rho)) : 0., sg = NOISE ? sqrt(P.amp_s * fabs(phi)) : 0.;
+    out[0 * oc + o] = 0.;
+    out[(long long)Q * oc + o] = 0.;
+#pragma unroll
+    for (int a = 1; a <= 3; ++a) {
+      const double v = aj * (double)n[a - 1];
+      out[(long long)a * oc + o] = v;
+      out[(long long)(Q + a) * oc + o] = -v;
+    }
+#pragma unroll
+    for (int a = 4; a < Q; ++a) {
+      out[(long long)a * oc + o] = (sqrt_bnorm(a) * sf) * (double)n[3 + 2 * (a - 4)];
+      out[(long long)(Q + a) * oc + o] = (sqrt_bnorm(a) * sg) * (double)n[4 + 2 * (a - 4)];
+    }
+    return;
+  }
+  if (MODE == OBS_HYDRO) {
+    double grho[3], gphi[3];
+    density_gradients(R, I, grho, gphi);
+    const float n3[3] = {n[0], n[1], n[2]};
+    const double jf[3] = {mf[1], mf[2], mf[3]}, jg[3] = {mg[1], mg[2], mg[3]};
+    CellHydro H;
+    cell_hydro<NOISE>(P, rho, phi, jf, jg, grho, gphi, n3, H);
+    out[0 * oc + o] = rho;
+    out[1 * oc + o] = phi;
+    out[5 * oc + o] = rho + phi;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      out[(2 + k) * oc + o] = H.uf[k];
+      out[(6 + k) * oc + o] = H.ug[k];
+      out[(9 + k) * oc + o] = H.af[k];
+      out[(12 + k) * oc + o] = H.ag[k];
+      out[(15 + k) * oc + o] = (rho * H.ufb[k] + phi * H.ugb[k] + 0.5 * (rho * H.af[k] + phi * H.ag[k])) * H.inv_tot;
+    }
+    out[18 * oc + o] = H.nfv[0];
+    out[19 * oc + o] = H.ngv[0];
+    out[20 * oc + o] = H.ufb[0];
+    out[21 * oc + o] = H.ugb[0];
+  }
+}
+
+// diagnostics: per-block partial sums {rho, phi, rho*x, rho*y, rho*zg} and count of non-finite hydro values
+__global__ void __launch_bounds__(256) k_diag(Geom G, const double2* __restrict__ R, double* __restrict__ partial,
+                                               unsigned long long* __restrict__ nonfinite) {
+  __shared__ double sh[5][256];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zl = blockIdx.z;
+  double v[5] = {0., 0., 0., 0., 0.};
+  if (x < G.nx && y < G.ny) {
+    const double2 r = R[(long long)(zl + 1) * G.plane + (long long)y * G.nx + x];
+    v[0] = r.x; v[1] = r.y; v[2] = r.x * x; v[3] = r.x * y; v[4] = r.x * (G.z0 + zl);
+    if (!(isfinite(r.x) && isfinite(r.y))) atomicAdd(nonfinite, 1ull);
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) sh[k][tid] = v[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) sh[k][tid] += sh[k][tid + s];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const long long b = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) partial[b * 5 + k] = sh[k][0];
+  }
+}
+__global__ void k_count_nonfinite(const double* __restrict__ a, long long n, unsigned long long* __restrict__ cnt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !isfinite(a[i])) atomicAdd(cnt, 1ull);
+}
+
+__global__ void k_philox_test(uint4 ctr, uint2 key, uint4* out) { *out = philox4x32(ctr, key); }
+
+}  // namespace bflbm

@@ -1,0 +1,69 @@
+// Counter-based Gaussian noise for the fluctuating collision.
+//
+// The reference draws 33 N(0,1) numbers per cell per step from amrex::RandomNormal
+// (LBM_binary.H:115-127): a=1..3 one draw each (shared by f and g with opposite sign), a=4..18 two
+// draws each (f then g).  Here draw d in that same order is a pure function of
+//     (seed, global cell index, step, d)
+// through Philox4x32-10 (Salmon et al., SC'11) and a Box-Muller transform evaluated in fp32 with the
+// hardware fast paths (MUFU lg2/sin/cos); the amplitude multiply is done in fp64 by the caller.
+// Results therefore do not depend on the decomposition (number of GPUs, tiling) or launch order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bflbm {
+
+#ifndef BFLBM_PHILOX_ROUNDS
+#define BFLBM_PHILOX_ROUNDS 10
+#endif
+
+__host__ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < BFLBM_PHILOX_ROUNDS; ++r) {
+#ifdef __CUDA_ARCH__
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), hi1 = __umulhi(0xCD9E8D57u, ctr.z);
+#else
+    const uint32_t hi0 = (uint32_t)(((uint64_t)0xD2511F53u * ctr.x) >> 32), hi1 = (uint32_t)(((uint64_t)0xCD9E8D57u * ctr.z) >> 32);
+#endif
+    const uint32_t lo0 = 0xD2511F53u * ctr.x, lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// two uniforms -> two independent standard normals
+__device__ __forceinline__ void box_muller(uint32_t u0, uint32_t u1, float& n0, float& n1) {
+  // U in (0,1]: (u0 + 0.5) / 2^32, tail down to 2^-33 (|n| <= 6.76)
+  const float U = fmaf((float)u0, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float r = sqrtf(-1.3862943611198906f * __log2f(U));           // sqrt(-2 ln U), ln U = ln2 * lg2 U
+  const float th = (float)(int32_t)u1 * 1.4629180792671596e-9f;      // pi * 2^-31 * s32  in [-pi, pi)
+  float s, c;
+  __sincosf(th, &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+
+// Philox counter layout: {cell_lo, cell_hi, step_lo, (step_hi & 0xffffff) | block << 24}, key = seed.
+// Block j yields draws 4j .. 4j+3.
+struct NoiseKey {
+  uint2 key;
+  uint32_t cell_lo, cell_hi, step_lo, step_hi;
+};
+__device__ __forceinline__ NoiseKey make_noise_key(unsigned long long seed, unsigned long long cell, long long step) {
+  NoiseKey k;
+  k.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  k.cell_lo = (uint32_t)cell;
+  k.cell_hi = (uint32_t)(cell >> 32);
+  k.step_lo = (uint32_t)(unsigned long long)step;
+  k.step_hi = (uint32_t)((unsigned long long)step >> 32) & 0x00ffffffu;
+  return k;
+}
+__device__ __forceinline__ void normals4(const NoiseKey& k, int block, float (&n)[4]) {
+  const uint4 r = philox4x32(make_uint4(k.cell_lo, k.cell_hi, k.step_lo, k.step_hi | ((uint32_t)block << 24)), k.key);
+  box_muller(r.x, r.y, n[0], n[1]);
+  box_muller(r.z, r.w, n[2], n[3]);
+}
+
+}  // namespace bflbm

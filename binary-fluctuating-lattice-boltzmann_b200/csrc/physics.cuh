@@ -1,0 +1,139 @@
+// Per-cell physics of the fluctuating binary (two-component Shan-Chen type) D3Q19 update.
+// What is computed follows the reference cell by cell (algebra in SURVEY.md 3.2b):
+//   hydrodynamic fields  LBM_binary.H:196-295 (hydrovars), :315-340 (hydrovars_bar_density)
+//   19-point gradient    LBM_binary.H:134-150
+//   noise amplitudes     LBM_binary.H:73-132
+//   equilibrium / force moments and the relaxation  LBM_binary.H:356-516
+// How it is computed is GPU-first: three reciprocals per cell instead of ~80 divisions, moments
+// m0..m3 reused for densities and momenta, equilibrium and forcing written directly in their
+// simplified algebraic form.  Agreement with the reference is at rounding level (tests: 1e-12).
+#pragma once
+#include <cfloat>
+#include "d3q19.cuh"
+#include "philox.cuh"
+
+namespace bflbm {
+
+struct DevParams {
+  double rate_f, rate_g;  // 1/(tau (1 + 0.5/tau))            LBM_binary.H:504-505
+  double fric_f, fric_g;  // 0.5/(tau + 0.5)                   LBM_binary.H:266-272
+  double force_pf;        // 1/(1 + 1/(2 tau_f)), both species LBM_binary.H:424
+  double acc_coef;        // -cs2 * alpha0                     LBM_binary.H:254-255
+  double amp_j;           // A kBT,      A = 2(l - l^2/2), l = 1/(tau_f + 1/2)   LBM_binary.H:79-82,117
+  double amp_s;           // A kBT / cs2                                          LBM_binary.H:125-126
+  unsigned long long seed;
+};
+
+struct CellHydro {
+  double rho, phi, inv_tot;
+  double ufb[3], ugb[3];  // LB ("bar") velocities j/rho
+  double af[3], ag[3];    // accelerations
+  double uf[3], ug[3];    // real species velocities (contain +xi/2)
+  double nfv[3], ngv[3];  // momentum noise / density
+  double xi[3];           // momentum-mode noise of species f (species g gets -xi)
+};
+
+// (1/cs2) sum_i w_i n(x+c_i) c_i ; n[i] = field at x + c_i (n[0] unused)
+__device__ __forceinline__ void gradient19(const double (&n)[Q], double (&g)[3]) {
+  g[0] = (1. / 6.) * (n[1] - n[2]) + (1. / 12.) * (((n[7] - n[8]) + (n[9] - n[10])) + ((n[15] - n[16]) + (n[17] - n[18])));
+  g[1] = (1. / 6.) * (n[3] - n[4]) + (1. / 12.) * (((n[7] - n[8]) - (n[9] - n[10])) + ((n[11] - n[12]) + (n[13] - n[14])));
+  g[2] = (1. / 6.) * (n[5] - n[6]) + (1. / 12.) * (((n[11] - n[12]) - (n[13] - n[14])) + ((n[15] - n[16]) - (n[17] - n[18])));
+}
+
+// n3: the first three standard normals of the cell (draws 0..2), ignored when !NOISE
+template <bool NOISE>
+__device__ __forceinline__ void cell_hydro(const DevParams& P, double rho, double phi, const double (&jf)[3], const double (&jg)[3],
+                                           const double (&grad_rho)[3], const double (&grad_phi)[3], const float (&n3)[3],
+                                           CellHydro& H) {
+  H.rho = rho;
+  H.phi = phi;
+  const bool has_f = fabs(rho) > (double)FLT_EPSILON, has_g = fabs(phi) > (double)FLT_EPSILON;
+  const double inv_rho = has_f ? 1. / rho : 0., inv_phi = has_g ? 1. / phi : 0.;
+  const double tot = rho + phi;
+  H.inv_tot = 1. / tot;  // unguarded, like the reference (LBM_binary.H:266-272, 286-288, 471)
+  double amp = 0.;
+  if (NOISE) amp = sqrt(P.amp_j * fabs(rho * phi * H.inv_tot));
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    H.ufb[k] = jf[k] * inv_rho;
+    H.ugb[k] = jg[k] * inv_phi;
+    H.af[k] = has_f ? P.acc_coef * grad_phi[k] : 0.;
+    H.ag[k] = has_g ? P.acc_coef * grad_rho[k] : 0.;
+    H.xi[k] = NOISE ? amp * (double)n3[k] : 0.;
+    H.nfv[k] = H.xi[k] * inv_rho;
+    H.ngv[k] = -H.xi[k] * inv_phi;
+    const double d = (H.ufb[k] - H.ugb[k]) + 0.5 * (H.af[k] - H.ag[k]);
+    H.uf[k] = H.ufb[k] + 0.5 * H.af[k] - P.fric_f * phi * H.inv_tot * d + 0.5 * H.nfv[k];
+    H.ug[k] = H.ugb[k] + 0.5 * H.ag[k] + P.fric_g * rho * H.inv_tot * d + 0.5 * H.ngv[k];
+  }
+}
+
+// m <- m + rate (meq(D, vb) - m) + Phi(D, u, a)   for one species (noise is added separately)
+__device__ __forceinline__ void relax_species(double rate, double pf, double D, const double (&vb)[3], const double (&u)[3],
+                                              const double (&a)[3], double (&m)[Q]) {
+  const double keep = 1. - rate;
+  const double Dr = D * rate, Dp = D * pf;
+  // momentum modes
+#pragma unroll
+  for (int k = 0; k < 3; ++k) m[1 + k] = keep * m[1 + k] + Dr * vb[k] + Dp * a[k];
+  // stress modes
+  const double vxx = vb[0] * vb[0], vyy = vb[1] * vb[1], vzz = vb[2] * vb[2];
+  const double axx = a[0] * u[0], ayy = a[1] * u[1], azz = a[2] * u[2];
+  const double tr = axx + ayy + azz;
+  m[4] = keep * m[4] + Dr * (vxx + vyy + vzz) + Dp * (2. * tr);
+  m[5] = keep * m[5] + Dr * (2. * vxx - vyy - vzz) + Dp * (6. * axx - 2. * tr);
+  m[6] = keep * m[6] + Dr * (vyy - vzz) + Dp * (2. * (ayy - azz));
+  m[7] = keep * m[7] + Dr * (vb[0] * vb[1]) + Dp * (a[0] * u[1] + a[1] * u[0]);
+  m[8] = keep * m[8] + Dr * (vb[1] * vb[2]) + Dp * (a[1] * u[2] + a[2] * u[1]);
+  m[9] = keep * m[9] + Dr * (vb[0] * vb[2]) + Dp * (a[0] * u[2] + a[2] * u[0]);
+  // ghost modes: no equilibrium, no force
+#pragma unroll
+  for (int k = 10; k < Q; ++k) m[k] = keep * m[k];
+}
+
+// full collision of one cell in moment space; mf, mg in: moments of the post-stream populations,
+// out: post-collision moments.  Returns the hydro fields used (for the observers).
+template <bool NOISE>
+__device__ __forceinline__ void collide_cell(const DevParams& P, const double (&grad_rho)[3], const double (&grad_phi)[3],
+                                             const NoiseKey& nk, double (&mf)[Q], double (&mg)[Q]) {
+  float n0[4] = {0.f, 0.f, 0.f, 0.f};
+  if (NOISE) normals4(nk, 0, n0);
+  const float n3[3] = {n0[0], n0[1], n0[2]};
+  const double jf[3] = {mf[1], mf[2], mf[3]}, jg[3] = {mg[1], mg[2], mg[3]};
+  CellHydro H;
+  cell_hydro<NOISE>(P, mf[0], mg[0], jf, jg, grad_rho, grad_phi, n3, H);
+  double vb[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) vb[k] = (H.rho * H.uf[k] + H.phi * H.ug[k]) * H.inv_tot;  // LBM_binary.H:471
+  relax_species(P.rate_f, P.force_pf, H.rho, vb, H.uf, H.af, mf);
+  relax_species(P.rate_g, P.force_pf, H.phi, vb, H.ug, H.ag, mg);
+  if (NOISE) {
+    // draws in the reference's order: d = 0..2 momentum (f: +, g: -), then for a = 4..18: f, g
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      mf[1 + k] += H.xi[k];
+      mg[1 + k] -= H.xi[k];
+    }
+    const double sf = sqrt(P.amp_s * fabs(H.rho)), sg = sqrt(P.amp_s * fabs(H.phi));
+    float nb[4] = {n0[0], n0[1], n0[2], n0[3]};
+#pragma unroll
+    for (int d = 3; d < 33; ++d) {
+      if ((d & 3) == 0) normals4(nk, d >> 2, nb);
+      const int a = 4 + ((d - 3) >> 1);
+      if (((d - 3) & 1) == 0) mf[a] += (sqrt_bnorm(a) * sf) * (double)nb[d & 3];
+      else                    mg[a] += (sqrt_bnorm(a) * sg) * (double)nb[d & 3];
+    }
+  }
+}
+
+// the 33 standard normals of a cell in reference draw order (observer / test hook)
+__device__ __forceinline__ void cell_normals(const NoiseKey& nk, float (&n)[36]) {
+#pragma unroll
+  for (int b = 0; b < 9; ++b) {
+    float t[4];
+    normals4(nk, b, t);
+    n[4 * b] = t[0]; n[4 * b + 1] = t[1]; n[4 * b + 2] = t[2]; n[4 * b + 3] = t[3];
+  }
+}
+
+}  // namespace bflbm

@@ -1,0 +1,347 @@
+"""Host-side mirror of the reference's solver interface over the C ABI (include/bflbm.h).
+
+The reference's boundary is a set of free functions on caller-owned MultiFabs
+(LBM_binary.H:545-551, 598-605, 632-641, 664-668, 699-707) plus global parameters
+(LBM_d3q19.H:10, LBM_binary.H:17-30).  `Lattice` bundles what those MultiFabs hold; the module-level
+functions at the bottom keep the reference's names and argument meaning.
+
+Every array is float64 with C shape (ncomp, nz_local, ny, nx) = AMReX FAB order.
+There is no CPU path: constructing a Lattice without the CUDA library or a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass, asdict
+
+import numpy as np
+
+from . import _build
+
+NVEL, NHYDRO, NHYDRO_BAR, NNORMALS = 19, 22, 9, 33
+
+#: hydrovs component names, AMReX_FileIO.H:208-261
+VARIABLE_NAMES = ["rho", "phi", "ufx", "ufy", "ufz", "p_bulk", "ugx", "ugy", "ugz", "afx", "afy", "afz",
+                  "agx", "agy", "agz", "ubx", "uby", "ubz", "nfbarx", "ngbarx", "ufbarx", "ugbarx"]
+
+
+class BflbmError(RuntimeError):
+    pass
+
+
+class _CParams(ctypes.Structure):
+    _fields_ = [("kBT", ctypes.c_double), ("tau_f", ctypes.c_double), ("tau_g", ctypes.c_double),
+                ("alpha0", ctypes.c_double), ("alpha1", ctypes.c_double), ("kappa", ctypes.c_double),
+                ("rho_lo", ctypes.c_double), ("rho_hi", ctypes.c_double),
+                ("seed", ctypes.c_ulonglong), ("step0", ctypes.c_longlong)]
+
+
+@dataclass
+class Params:
+    """The reference's editable globals (defaults = shipped values)."""
+    kBT: float = 0.0       # LBM_d3q19.H:10
+    tau_f: float = 0.5     # LBM_binary.H:18
+    tau_g: float = 0.5     # LBM_binary.H:19
+    alpha0: float = 4.0    # LBM_binary.H:20
+    alpha1: float = 0.0    # LBM_binary.H:21 (no effect in the reference; must stay 0)
+    kappa: float = 4.0     # LBM_binary.H:30
+    rho_lo: float = 0.0    # LBM_binary.H:25
+    rho_hi: float = 1.0    # LBM_binary.H:26
+    seed: int = 12345      # LBM_binary.H:17 / main_run_job.cpp:68
+    step0: int = 0         # main_run_job.cpp:80 step_continue
+
+    def _c(self) -> _CParams:
+        return _CParams(**asdict(self))
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libbflbm.so (built in-tree by `_build.build()`); raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        raise BflbmError(f"CUDA library {path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU fallback)")
+    lib = ctypes.CDLL(path)
+    vp, ip, dp = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    P = ctypes.POINTER(_CParams)
+    sig = {
+        "bflbm_params_default": (ip, [P]),
+        "bflbm_create": (ip, [P, ip, ip, ip, ip, ctypes.POINTER(vp)]),
+        "bflbm_create_slab": (ip, [P, ip, ip, ip, ip, ip, ip, ctypes.POINTER(vp)]),
+        "bflbm_destroy": (ip, [vp]),
+        "bflbm_set_params": (ip, [vp, P]),
+        "bflbm_get_params": (ip, [vp, P]),
+        "bflbm_set_stream": (ip, [vp, vp]),
+        "bflbm_set_algorithm": (ip, [vp, ip]),
+        "bflbm_set_tiling": (ip, [vp, ip]),
+        "bflbm_init_mixture": (ip, [vp]),
+        "bflbm_init_stripe": (ip, [vp, dp]),
+        "bflbm_init_droplet": (ip, [vp, dp]),
+        "bflbm_init_from_populations": (ip, [vp, vp, vp]),
+        "bflbm_init_from_populations_slab": (ip, [vp, vp, vp]),
+        "bflbm_step": (ip, [vp, ip]),
+        "bflbm_sync": (ip, [vp]),
+        "bflbm_step_count": (ctypes.c_longlong, [vp]),
+        "bflbm_get_populations": (ip, [vp, vp, vp]),
+        "bflbm_get_hydrovars": (ip, [vp, vp]),
+        "bflbm_get_hydrovars_bar": (ip, [vp, vp]),
+        "bflbm_get_noise": (ip, [vp, vp, vp]),
+        "bflbm_get_normals": (ip, [vp, vp]),
+        "bflbm_get_hydrovars_device": (ip, [vp, vp]),
+        "bflbm_get_hydrovars_bar_device": (ip, [vp, vp]),
+        "bflbm_get_populations_device": (ip, [vp, vp, vp]),
+        "bflbm_center_of_mass": (ip, [vp, vp, vp]),
+        "bflbm_total_mass": (ip, [vp, vp, vp]),
+        "bflbm_check_nan": (ip, [vp, ctypes.POINTER(ctypes.c_longlong)]),
+        "bflbm_halo_doubles": (ctypes.c_size_t, [vp]),
+        "bflbm_halo_send_buffer": (vp, [vp, ip]),
+        "bflbm_halo_recv_buffer": (vp, [vp, ip]),
+        "bflbm_step_begin": (ip, [vp]),
+        "bflbm_step_end": (ip, [vp]),
+        "bflbm_halo_refresh_begin": (ip, [vp]),
+        "bflbm_halo_refresh_end": (ip, [vp]),
+        "bflbm_set_profiling": (ip, [vp, ip]),
+        "bflbm_get_profile": (ip, [vp, vp, ctypes.POINTER(ctypes.c_longlong)]),
+        "bflbm_kernel_launches": (ctypes.c_longlong, [vp]),
+        "bflbm_device_bytes": (ctypes.c_size_t, [vp]),
+        "bflbm_debug_philox": (ip, [vp, vp, vp]),
+        "bflbm_last_error": (ctypes.c_char_p, []),
+        "bflbm_version": (ctypes.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise BflbmError(f"bflbm error {rc}: {load_library().bflbm_last_error().decode()}")
+
+
+def _host(a, shape, name):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.shape != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {a.shape}")
+    return a
+
+
+class Lattice:
+    """Device-resident state of one box (or one z-slab of it): what fold, gold, hydrovs, hydrovsbar,
+    fnoisevs, gnoisevs hold in the reference (main_run_job.cpp:205-212)."""
+
+    def __init__(self, nx, ny=None, nz=None, params: Params | None = None, device: int = 0,
+                 slab: tuple[int, int] | None = None):
+        ny = nx if ny is None else ny
+        nz = nx if nz is None else nz
+        self.lib = load_library()
+        self.params = params or Params()
+        self.nx, self.ny, self.nz_global = int(nx), int(ny), int(nz)
+        self.z0, self.nz = (0, self.nz_global) if slab is None else (int(slab[0]), int(slab[1]))
+        self.shape = (self.nz, self.ny, self.nx)
+        self.device = device
+        h = ctypes.c_void_p()
+        cp = self.params._c()
+        if slab is None:
+            _check(self.lib.bflbm_create(ctypes.byref(cp), self.nx, self.ny, self.nz_global, device, ctypes.byref(h)))
+        else:
+            _check(self.lib.bflbm_create_slab(ctypes.byref(cp), self.nx, self.ny, self.nz_global, self.z0, self.nz,
+                                              device, ctypes.byref(h)))
+        self.h = h
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bflbm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- parameters -------------------------------------------------------------------------------
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise AttributeError(k)
+            setattr(self.params, k, v)
+        cp = self.params._c()
+        _check(self.lib.bflbm_set_params(self.h, ctypes.byref(cp)))
+
+    def set_stream(self, cuda_stream: int | None):
+        _check(self.lib.bflbm_set_stream(self.h, ctypes.c_void_p(cuda_stream or 0)))
+
+    def set_algorithm(self, name: str):
+        _check(self.lib.bflbm_set_algorithm(self.h, {"fused": 0, "twopass": 1}[name]))
+
+    def set_tiling(self, lz: int):
+        _check(self.lib.bflbm_set_tiling(self.h, int(lz)))
+
+    # -- initial conditions -------------------------------------------------------------------------
+    def init_mixture(self):
+        _check(self.lib.bflbm_init_mixture(self.h))
+
+    def init_stripe(self, frac=0.5):
+        _check(self.lib.bflbm_init_stripe(self.h, float(frac)))
+
+    def init_droplet(self, radius=0.2):
+        _check(self.lib.bflbm_init_droplet(self.h, float(radius)))
+
+    def init_from_populations(self, f, g):
+        f = _host(f, (NVEL,) + self.shape, "f")
+        g = _host(g, (NVEL,) + self.shape, "g")
+        _check(self.lib.bflbm_init_from_populations(self.h, f.ctypes.data, g.ctypes.data))
+
+    def init_from_populations_slab(self, f_ghosted, g_ghosted):
+        shp = (NVEL, self.nz + 2, self.ny, self.nx)
+        f = _host(f_ghosted, shp, "f_ghosted")
+        g = _host(g_ghosted, shp, "g_ghosted")
+        _check(self.lib.bflbm_init_from_populations_slab(self.h, f.ctypes.data, g.ctypes.data))
+
+    # -- time stepping --------------------------------------------------------------------------------
+    def step(self, n=1):
+        _check(self.lib.bflbm_step(self.h, int(n)))
+
+    def sync(self):
+        _check(self.lib.bflbm_sync(self.h))
+
+    @property
+    def step_count(self) -> int:
+        return int(self.lib.bflbm_step_count(self.h))
+
+    # -- outputs --------------------------------------------------------------------------------------
+    def populations(self):
+        f = np.empty((NVEL,) + self.shape)
+        g = np.empty((NVEL,) + self.shape)
+        _check(self.lib.bflbm_get_populations(self.h, f.ctypes.data, g.ctypes.data))
+        return f, g
+
+    def hydrovars(self):
+        out = np.empty((NHYDRO,) + self.shape)
+        _check(self.lib.bflbm_get_hydrovars(self.h, out.ctypes.data))
+        return out
+
+    def hydrovars_bar(self):
+        out = np.empty((NHYDRO_BAR,) + self.shape)
+        _check(self.lib.bflbm_get_hydrovars_bar(self.h, out.ctypes.data))
+        return out
+
+    def noise(self):
+        fn = np.empty((NVEL,) + self.shape)
+        gn = np.empty((NVEL,) + self.shape)
+        _check(self.lib.bflbm_get_noise(self.h, fn.ctypes.data, gn.ctypes.data))
+        return fn, gn
+
+    def normals(self):
+        out = np.empty(self.shape + (NNORMALS,))
+        _check(self.lib.bflbm_get_normals(self.h, out.ctypes.data))
+        return out
+
+    def center_of_mass(self):
+        com = (ctypes.c_double * 3)()
+        sums = (ctypes.c_double * 4)()
+        _check(self.lib.bflbm_center_of_mass(self.h, com, sums))
+        return np.array(com), np.array(sums)
+
+    def total_mass(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        _check(self.lib.bflbm_total_mass(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def check_nan(self) -> int:
+        """Number of non-finite hydro values; raises BflbmError if any (the reference prints and exit(0)s,
+        Debug.H:137-149)."""
+        n = ctypes.c_longlong()
+        rc = self.lib.bflbm_check_nan(self.h, ctypes.byref(n))
+        _check(rc)
+        return n.value
+
+    def set_profiling(self, on: bool):
+        _check(self.lib.bflbm_set_profiling(self.h, int(bool(on))))
+
+    def profile(self):
+        """(ms per step of {step kernel, density fold, halo pack, halo unpack}, steps accumulated)"""
+        ms = (ctypes.c_double * 4)()
+        n = ctypes.c_longlong()
+        _check(self.lib.bflbm_get_profile(self.h, ms, ctypes.byref(n)))
+        k = max(1, n.value)
+        return [v / k for v in ms], n.value
+
+    # -- bookkeeping ----------------------------------------------------------------------------------
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.bflbm_kernel_launches(self.h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.bflbm_device_bytes(self.h))
+
+
+def philox4x32_10(ctr, key):
+    """Device-side Philox4x32-10 block (known-answer test hook)."""
+    lib = load_library()
+    c = (ctypes.c_uint * 4)(*ctr)
+    k = (ctypes.c_uint * 2)(*key)
+    o = (ctypes.c_uint * 4)()
+    _check(lib.bflbm_debug_philox(c, k, o))
+    return tuple(int(v) for v in o)
+
+
+# ---- the reference's function names (LBM_binary.H) ---------------------------------------------------
+def LBM_init_mixture(lat: Lattice):
+    """LBM_binary.H:598-629"""
+    lat.init_mixture()
+
+
+def LBM_init_stripe(frac: float, lat: Lattice):
+    """LBM_binary.H:663-695"""
+    lat.init_stripe(frac)
+
+
+def LBM_init_droplet(r: float, lat: Lattice):
+    """LBM_binary.H:698-742"""
+    lat.init_droplet(r)
+
+
+def LBM_init(lat: Lattice, f0, g0):
+    """LBM_binary.H:631-661 (restart from populations)"""
+    lat.init_from_populations(f0, g0)
+
+
+def LBM_timestep(lat: Lattice, nsteps: int = 1):
+    """LBM_binary.H:544-594"""
+    lat.step(nsteps)
+
+
+def LBM_hydrovars(lat: Lattice):
+    """LBM_binary.H:297-313: the 22 real hydrodynamic fields"""
+    return lat.hydrovars()
+
+
+def LBM_hydrovars_density(lat: Lattice):
+    """LBM_binary.H:342-354: hydrovsbar components 0..8"""
+    return lat.hydrovars_bar()
+
+
+def thermal_noise(lat: Lattice):
+    """LBM_binary.H:73-132: (fnoise, gnoise) for the next collision"""
+    return lat.noise()
+
+
+def update_com(lat: Lattice):
+    """LBM_hydrovs.H:26-60"""
+    return lat.center_of_mass()[0]

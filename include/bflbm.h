@@ -1,0 +1,168 @@
+/* bflbm.h -- C ABI of the B200-native fluctuating binary D3Q19 lattice-Boltzmann step.
+ *
+ * This is the drop-in boundary for ONE hot path of MDProject/Binary-Fluctuating-Lattice-Boltzmann:
+ * the per-step update in LBM_binary.H / LBM_d3q19.H.  The reference has no FFI; its boundary is a
+ * set of header-inline C++ functions on caller-owned amrex::MultiFab objects plus global parameters.
+ * Each entry point below names the reference interface it replaces (file:line in the reference).
+ *
+ * Conventions
+ *  - Device memory is owned by the library; host buffers by the caller.
+ *  - Host arrays are float64 in AMReX FAB order for the VALID region: x fastest, then y, z,
+ *    component slowest, i.e. C shape (ncomp, nz_local, ny, nx).
+ *  - Every call returns 0 on success or a negative bflbm_status; bflbm_last_error() gives the text.
+ *    The library never calls exit() (the reference's NaN check does: Debug.H:137-149).
+ *  - A lattice may be the whole periodic box (bflbm_create) or one z-slab of it (bflbm_create_slab);
+ *    slabs exchange one ghost message per step through the bflbm_halo_* calls.
+ *  - "time" convention: after n calls of the reference's LBM_timestep
+ *    the MultiFabs hold post-stream populations of time n and hydrovs/noise derived from them;
+ *    all bflbm_get_* calls return exactly those quantities after n steps.
+ *  - There is no CPU fallback: every entry point fails with BFLBM_ERR_CUDA if no sm_100 device
+ *    can be used.
+ */
+#ifndef BFLBM_H_
+#define BFLBM_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFLBM_NVEL 19      /* LBM_d3q19.H:4 */
+#define BFLBM_NHYDRO 22    /* main_run_job.cpp:147, names in AMReX_FileIO.H:208-261 */
+#define BFLBM_NHYDRO_BAR 9 /* components of hydrovsbar that are ever written: LBM_binary.H:329-339 */
+#define BFLBM_NNORMALS 33  /* Gaussian draws per cell per step: LBM_binary.H:115-127 */
+
+typedef enum {
+  BFLBM_OK = 0,
+  BFLBM_ERR_ARG = -1,    /* bad argument / unsupported parameter (e.g. alpha1 != 0, use_SC_pseudo) */
+  BFLBM_ERR_CUDA = -2,   /* CUDA runtime error or no usable device */
+  BFLBM_ERR_STATE = -3,  /* call order (e.g. step before init) */
+  BFLBM_ERR_NAN = -4     /* returned by bflbm_check_nan when a NaN/Inf is present */
+} bflbm_status;
+
+/* Every tunable the reference exposes by editing source.
+ * kBT: LBM_d3q19.H:10.  seed, tau_f, tau_g, alpha0, alpha1, rho_lo, rho_hi, kappa: LBM_binary.H:17-30.
+ * alpha1 does not enter the dynamics in the reference (LBM_binary.H:256-257 commented out); must be 0.
+ * step0: value of the step counter at creation (main_run_job.cpp:80 step_continue); the noise is a
+ *        pure function of (seed, global cell, step, draw) so a restart with the same step0 continues
+ *        the same random sequence (the reference does not checkpoint its RNG state). */
+typedef struct bflbm_params {
+  double kBT;
+  double tau_f, tau_g;
+  double alpha0, alpha1;
+  double kappa;
+  double rho_lo, rho_hi;
+  unsigned long long seed;
+  long long step0;
+} bflbm_params;
+
+typedef struct bflbm_lattice bflbm_lattice; /* opaque */
+
+/* shipped defaults: kBT 0, tau 1/2, alpha0 4, alpha1 0, kappa 4, rho in [0,1], seed 12345 */
+int bflbm_params_default(bflbm_params* p);
+
+/* Whole periodic box nx*ny*nz on CUDA device `device`.
+ * Replaces the MultiFab allocation block main_run_job.cpp:190-212 (fold,fnew,gold,gnew,hydrovs,
+ * hydrovsbar,fnoisevs,gnoisevs; nghost=2). */
+int bflbm_create(const bflbm_params* p, int nx, int ny, int nz, int device, bflbm_lattice** out);
+
+/* One z-slab [z0, z0+nz_local) of a periodic box nx*ny*nz_global.  Replaces BoxArray::maxSize +
+ * DistributionMapping (main_run_job.cpp:140-143) by a 1-D slab decomposition. */
+int bflbm_create_slab(const bflbm_params* p, int nx, int ny, int nz_global, int z0, int nz_local, int device,
+                      bflbm_lattice** out);
+int bflbm_destroy(bflbm_lattice* h);
+
+/* Run-time change of the reference's global parameters (they are plain globals there). */
+int bflbm_set_params(bflbm_lattice* h, const bflbm_params* p);
+int bflbm_get_params(const bflbm_lattice* h, bflbm_params* p);
+
+/* Use the caller's CUDA stream (a cudaStream_t) for all subsequent work; NULL = the library's own. */
+int bflbm_set_stream(bflbm_lattice* h, void* cuda_stream);
+/* 0 = one-pass fused step (default), 1 = two-pass step (density kernel + collide/stream kernel). */
+int bflbm_set_algorithm(bflbm_lattice* h, int algo);
+/* Height (planes) of the CTA bricks of the fused step; 0 = automatic.  Results are bit-identical for any
+ * number of slabs as long as every slab uses the same brick height and it divides nz_local. */
+int bflbm_set_tiling(bflbm_lattice* h, int brick_lz);
+
+/* LBM_init_mixture  LBM_binary.H:598-629 */
+int bflbm_init_mixture(bflbm_lattice* h);
+/* LBM_init_stripe   LBM_binary.H:663-695 (frac = main_run_job.cpp:33 init_frac) */
+int bflbm_init_stripe(bflbm_lattice* h, double frac);
+/* LBM_init_droplet  LBM_binary.H:698-742 (radius = main_run_job.cpp:110) */
+int bflbm_init_droplet(bflbm_lattice* h, double radius);
+/* LBM_init (restart) LBM_binary.H:631-661.  f,g: host, (19, nz_local, ny, nx); whole-box lattices only. */
+int bflbm_init_from_populations(bflbm_lattice* h, const double* f, const double* g);
+/* Same for a slab: arrays carry one extra plane below and above, (19, nz_local+2, ny, nx), holding the
+ * periodic neighbours' boundary planes (what FillBoundary would put in the first ghost layer). */
+int bflbm_init_from_populations_slab(bflbm_lattice* h, const double* f_ghosted, const double* g_ghosted);
+
+/* LBM_timestep  LBM_binary.H:544-594, nsteps times.  Asynchronous on the lattice's stream.
+ * For a slab lattice use bflbm_step_begin / halo exchange / bflbm_step_end instead. */
+int bflbm_step(bflbm_lattice* h, int nsteps);
+int bflbm_sync(bflbm_lattice* h);
+long long bflbm_step_count(const bflbm_lattice* h);
+
+/* fold/gold after the last step (post-stream populations): what the checkpoint writer reads,
+ * main_run_job.cpp:399-409. */
+int bflbm_get_populations(bflbm_lattice* h, double* f, double* g);
+/* hydrovs, 22 components in VariableNames order (AMReX_FileIO.H:208-261; values LBM_binary.H:216-294). */
+int bflbm_get_hydrovars(bflbm_lattice* h, double* out22);
+/* hydrovsbar components 0-8: rho, phi, ubar_f xyz, rho+phi, ubar_g xyz (LBM_binary.H:329-339). */
+int bflbm_get_hydrovars_bar(bflbm_lattice* h, double* out9);
+/* fnoisevs/gnoisevs for the NEXT collision (what WriteOutNoise dumps: Debug.H:380-409). */
+int bflbm_get_noise(bflbm_lattice* h, double* fn, double* gn);
+/* The 33 standard normals per cell behind bflbm_get_noise, shape (nz_local, ny, nx, 33), in the
+ * reference's draw order (LBM_binary.H:115-127).  Test hook: lets the CPU oracle be driven with the
+ * GPU's random numbers. */
+int bflbm_get_normals(bflbm_lattice* h, double* out33);
+/* Same getters into DEVICE memory owned by the caller (full local size, same layout). */
+int bflbm_get_hydrovars_device(bflbm_lattice* h, double* dev_out22);
+int bflbm_get_hydrovars_bar_device(bflbm_lattice* h, double* dev_out9);
+int bflbm_get_populations_device(bflbm_lattice* h, double* dev_f, double* dev_g);
+
+/* update_com  LBM_hydrovs.H:26-60 (centre of mass of rho; local-slab partial sums:
+ * sums4 = {mass, sum rho*x, sum rho*y, sum rho*z_global}). */
+int bflbm_center_of_mass(bflbm_lattice* h, double* com3, double* sums4);
+/* sums of rho and phi over the local cells (Debug.H:35-72 / main_run_job.cpp:224-228) */
+int bflbm_total_mass(bflbm_lattice* h, double* mass_rho, double* mass_phi);
+/* MultiFabNANCheck  Debug.H:136-149: counts non-finite values in the 22 hydro fields.
+ * Returns BFLBM_ERR_NAN if count > 0 (never exits). */
+int bflbm_check_nan(bflbm_lattice* h, long long* count);
+
+/* ---- slab halo exchange (replaces the 7 FillBoundary calls per step, LBM_binary.H:130-131,312,353,
+ * 553-555, by ONE message per neighbour per step) -------------------------------------------------
+ * side 0 = towards lower z, side 1 = towards higher z.  A message is bflbm_halo_doubles() float64s.
+ *   bflbm_step_begin : collide+stream on the slab, then pack both outgoing messages
+ *   (caller moves send(side) of rank r to recv(1-side) of the neighbour: NCCL send/recv or P2P)
+ *   bflbm_step_end   : unpack both messages, finish the density field; the step counter advances.
+ * bflbm_halo_refresh_begin/_end do the same exchange without stepping (after an init). */
+size_t bflbm_halo_doubles(const bflbm_lattice* h);
+void* bflbm_halo_send_buffer(bflbm_lattice* h, int side); /* device pointers, valid for the lattice's life */
+void* bflbm_halo_recv_buffer(bflbm_lattice* h, int side);
+int bflbm_step_begin(bflbm_lattice* h);
+int bflbm_step_end(bflbm_lattice* h);
+int bflbm_halo_refresh_begin(bflbm_lattice* h);
+int bflbm_halo_refresh_end(bflbm_lattice* h);
+
+/* Per-kernel device timing (CUDA events on the lattice's stream around each launch of a step):
+ * ms4 = accumulated milliseconds of {collide+stream kernel, density fold / density pass, halo pack, halo unpack},
+ * steps = steps accumulated since profiling was switched on.  Off by default (events serialise nothing but
+ * cost a little launch overhead). */
+int bflbm_set_profiling(bflbm_lattice* h, int on);
+int bflbm_get_profile(bflbm_lattice* h, double ms4[4], long long* steps);
+
+/* bookkeeping for bench.py: kernels launched by this lattice since creation, and device bytes held */
+long long bflbm_kernel_launches(const bflbm_lattice* h);
+size_t bflbm_device_bytes(const bflbm_lattice* h);
+
+/* Philox4x32-10 block function (test hook for known-answer vectors; runs on the device). */
+int bflbm_debug_philox(const unsigned int ctr[4], const unsigned int key[2], unsigned int out[4]);
+
+const char* bflbm_last_error(void);
+const char* bflbm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFLBM_H_ */

@@ -1,0 +1,286 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerance (BASELINE.json north_star): with kT = 0 the rho, phi and u fields agree within 1e-12 relative
+per step, measured as max|delta| / max|field| over a group of components that share a scale, from an
+IDENTICAL state (one-step restart).  With noise on, the GPU's own normals are injected into the oracle
+(bflbm_get_normals), which turns the fluctuating step into the same deterministic check.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_hydro_close, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+ALGOS = ["fused", "twopass"]
+
+
+def params_of(d):
+    return {k[2:]: float(d[k]) for k in d.files if k.startswith("p_")}
+
+
+def make_lattice(bflbm, shape, params, algo="fused", lz=None, **kw):
+    nx, ny, nz = shape
+    P = bflbm.Params(**{**params, **kw})
+    lat = bflbm.Lattice(nx, ny, nz, params=P)
+    lat.set_algorithm(algo)
+    if lz:
+        lat.set_tiling(lz)
+    return lat
+
+
+def test_philox_kat_on_device(bflbm):
+    from test_abi import PHILOX_KAT
+    for ctr, key, want in PHILOX_KAT:
+        assert bflbm.philox4x32_10(ctr, key) == want
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("path", [p for p in GOLDEN if "noise" not in p], ids=lambda p: os.path.basename(p)[:-4])
+def test_one_step_restart_vs_golden(bflbm, path, algo):
+    """From the fixture's initial populations: every step, restarted from the REFERENCE state of the step before."""
+    d = np.load(path)
+    shape = [int(v) for v in d["shape"]]
+    steps = [0] + [int(s) for s in d["steps"]]
+    prm = params_of(d)
+    with make_lattice(bflbm, shape, prm, algo) as lat:
+        # state 0: observers reproduce hydrovs / hydrovsbar of the reference's LBM_init
+        lat.init_from_populations(d["f0"], d["g0"])
+        f, g = lat.populations()
+        assert np.array_equal(f, d["f0"]) and np.array_equal(g, d["g0"]), "get_populations must return what was put in"
+        assert_hydro_close(lat.hydrovars(), d["h0"], TOL, "init")
+        assert rel_err(lat.hydrovars_bar()[[0, 1, 5]], d["hb0"][[0, 1, 5]]) <= TOL
+        # consecutive fixture states that are exactly one step apart
+        for a, b in zip(steps[:-1], steps[1:]):
+            if b - a != 1:
+                continue
+            fa, ga = (d["f0"], d["g0"]) if a == 0 else (d[f"f_{a}"], d[f"g_{a}"])
+            lat.init_from_populations(fa, ga)
+            lat.step(1)
+            f, g = lat.populations()
+            assert rel_err(f, d[f"f_{b}"]) <= TOL and rel_err(g, d[f"g_{b}"]) <= TOL
+            assert_hydro_close(lat.hydrovars(), d[f"h_{b}"], TOL, f"step {b}")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("path", [p for p in GOLDEN if "noise" not in p], ids=lambda p: os.path.basename(p)[:-4])
+def test_free_running_vs_golden(bflbm, path, algo):
+    d = np.load(path)
+    shape = [int(v) for v in d["shape"]]
+    with make_lattice(bflbm, shape, params_of(d), algo) as lat:
+        lat.init_from_populations(d["f0"], d["g0"])
+        done = 0
+        for s in [int(v) for v in d["steps"]]:
+            lat.step(s - done)
+            done = s
+            f, g = lat.populations()
+            assert rel_err(f, d[f"f_{s}"]) <= 10 * TOL and rel_err(g, d[f"g_{s}"]) <= 10 * TOL
+            assert_hydro_close(lat.hydrovars(), d[f"h_{s}"], 10 * TOL, f"step {s}")
+            hb = lat.hydrovars_bar()
+            assert rel_err(hb[[0, 1, 5]], d[f"hb_{s}"][[0, 1, 5]]) <= 10 * TOL
+            vscale = max(np.abs(d[f"hb_{s}"][[2, 3, 4, 6, 7, 8]]).max(), 1e-4)
+            assert np.abs(hb[[2, 3, 4, 6, 7, 8]] - d[f"hb_{s}"][[2, 3, 4, 6, 7, 8]]).max() <= 10 * TOL * vscale
+        assert lat.step_count == done
+
+
+@pytest.mark.parametrize("init,arg", [("stripe", 0.5), ("droplet", 0.2), ("droplet", 0.3), ("mixture", None)])
+@pytest.mark.parametrize("shape", [(32, 32, 32), (8, 24, 20), (20, 12, 33)])
+def test_analytic_inits_vs_oracle(bflbm, oracle_mod, init, arg, shape):
+    """LBM_init_mixture / _stripe / _droplet incl. the integer divisions and box[0]-for-z quirk on odd / non-cubic boxes."""
+    prm = dict(kBT=0.0, tau_f=0.5, tau_g=0.5, alpha0=1.5, alpha1=0.0, kappa=0.6, rho_lo=0.1, rho_hi=3.0)
+    O = oracle_mod.PortOracle(*shape)
+    O.set_params(**prm)
+    args = [] if arg is None else [arg]
+    getattr(O, "init_" + init)(*args)
+    with make_lattice(bflbm, shape, prm) as lat:
+        getattr(lat, "init_" + init)(*args)
+        f, g = lat.populations()
+        fo, go = O.populations()
+        # device tanh vs glibc tanh: a few ulp
+        assert rel_err(f, fo) <= 1e-14 and rel_err(g, go) <= 1e-14
+        assert_hydro_close(lat.hydrovars(), O.hydrovars(), TOL, "init")
+        lat.step(3)
+        O.step(3)
+        assert_hydro_close(lat.hydrovars(), O.hydrovars(), 10 * TOL, "3 steps")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_config1_flat_interface_32cubed(bflbm, oracle_mod, algo):
+    """BASELINE config 1: flat interface 32^3, kT = 0.  Per-step (one-step restart) parity at steps
+    0, 1, 10, 50 of the oracle trajectory, and the free-running state after 100 steps."""
+    shape = (32, 32, 32)
+    for prm in (dict(kBT=0.0, tau_f=0.5, tau_g=0.5, alpha0=4.0, alpha1=0.0, kappa=4.0, rho_lo=0.0, rho_hi=1.0),
+                dict(kBT=0.0, tau_f=0.5, tau_g=0.5, alpha0=1.5, alpha1=0.0, kappa=0.1, rho_lo=0.1, rho_hi=3.0)):
+        O = oracle_mod.PortOracle(*shape)
+        O.set_params(**prm)
+        O.init_stripe(0.5)
+        f0, g0 = O.populations()
+        with make_lattice(bflbm, shape, prm, algo) as lat, make_lattice(bflbm, shape, prm, algo) as free:
+            free.init_from_populations(f0, g0)
+            done = 0
+            for s in (0, 1, 10, 50):
+                O.step(s - done)
+                free.step(s - done)
+                done = s
+                fo, go = O.populations()
+                lat.init_from_populations(fo, go)
+                lat.step(1)
+                O.step(1)
+                free.step(1)
+                done += 1
+                assert_hydro_close(lat.hydrovars(), O.hydrovars(), TOL, f"restart at {s}")
+                fl, gl = lat.populations()
+                fo, go = O.populations()
+                assert rel_err(fl, fo) <= TOL and rel_err(gl, go) <= TOL
+            O.step(100 - done)
+            free.step(100 - done)
+            # free-running: rounding differences are not amplified for this relaxing interface
+            assert_hydro_close(free.hydrovars(), O.hydrovars(), 1e-10, "free-running 100 steps")
+            m0 = f0.sum(), g0.sum()
+            m = free.total_mass()
+            assert abs(m[0] - m0[0]) <= 1e-12 * m0[0] and abs(m[1] - m0[1]) <= 1e-12 * m0[1]
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("path", [p for p in GOLDEN if "noise" in p], ids=lambda p: os.path.basename(p)[:-4])
+def test_noise_amplitudes_vs_golden(bflbm, path, algo):
+    """The reference's noise fields for given (rho, phi) and given normals: amplitude law of LBM_binary.H:113-127.
+    GPU noise / GPU normals must reproduce fn / normals of the fixture (same state => same amplitudes)."""
+    d = np.load(path)
+    shape = [int(v) for v in d["shape"]]
+    with make_lattice(bflbm, shape, params_of(d), algo) as lat:
+        lat.init_from_populations(d["f_1"], d["g_1"])
+        fn, gn = lat.noise()
+        n = lat.normals()  # (nz, ny, nx, 33)
+        ref_n = d["normals"][1]  # normals fed before step 1 = the draws of the noise generated at the END of step 1
+        with np.errstate(divide="ignore", invalid="ignore"):
+            amp_f = d["fn_1"] / np.moveaxis(ref_n, -1, 0)[[0, 0, 1, 2] + [3 + 2 * (a - 4) for a in range(4, 19)]]
+            amp_g = d["gn_1"] / np.moveaxis(ref_n, -1, 0)[[0, 0, 1, 2] + [4 + 2 * (a - 4) for a in range(4, 19)]]
+        nn = np.moveaxis(n, -1, 0)
+        for a in range(1, 19):
+            df = 3 + 2 * (a - 4) if a >= 4 else a - 1
+            dg = 4 + 2 * (a - 4) if a >= 4 else a - 1
+            assert rel_err(fn[a], amp_f[a] * nn[df]) <= 1e-12, f"fn[{a}]"
+            assert rel_err(gn[a], amp_g[a] * nn[dg]) <= 1e-12, f"gn[{a}]"
+        assert not fn[0].any() and not gn[0].any()
+        assert np.array_equal(gn[1:4], -fn[1:4])
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("tau", [(0.5, 0.5), (0.8, 0.6)])
+def test_fluctuating_step_with_injected_normals(bflbm, oracle_mod, algo, tau):
+    """Noise on: drive the oracle with the GPU's normals; populations, noise and all 22 hydro fields (the real
+    velocities contain xi/2, LBM_binary.H:266-272) must then agree to 1e-12 for several consecutive steps."""
+    shape = (12, 10, 14)
+    prm = dict(kBT=1e-5, tau_f=tau[0], tau_g=tau[1], alpha0=1.5, alpha1=0.0, kappa=0.1, rho_lo=0.1, rho_hi=3.0)
+    with make_lattice(bflbm, shape, prm, algo, seed=2024, step0=17) as lat:
+        lat.init_droplet(0.3)
+        f0, g0 = lat.populations()
+        O = oracle_mod.PortOracle(*shape)
+        O.set_params(**prm)
+        O.set_normals(lat.normals())
+        O.init_from_populations(f0, g0)
+        assert_hydro_close(lat.hydrovars(), O.hydrovars(), TOL, "init")
+        for s in range(4):
+            fn, gn = lat.noise()
+            fo, go = O.noise()
+            assert rel_err(fn, fo) <= TOL and rel_err(gn, go) <= TOL
+            lat.step(1)
+            O.set_normals(lat.normals())  # normals of the noise generated at the end of this step
+            O.step(1)
+            fl, gl = lat.populations()
+            fo, go = O.populations()
+            assert rel_err(fl, fo) <= 10 * TOL and rel_err(gl, go) <= 10 * TOL, f"step {s}"
+            assert_hydro_close(lat.hydrovars(), O.hydrovars(), 10 * TOL, f"step {s}")
+        assert lat.step_count == 17 + 4
+
+
+def test_normals_are_standard_and_keyed(bflbm):
+    """Counter-based noise: N(0,1) moments, independence across draws/cells/steps, reproducibility, seed/step keys."""
+    prm = dict(kBT=1e-5)
+    with make_lattice(bflbm, (32, 32, 32), prm, seed=1) as a, make_lattice(bflbm, (32, 32, 32), prm, seed=1) as b, \
+            make_lattice(bflbm, (32, 32, 32), prm, seed=2) as c:
+        for lat in (a, b, c):
+            lat.init_mixture()
+        na, nb, nc = a.normals(), b.normals(), c.normals()
+        assert np.array_equal(na, nb), "same (seed, cell, step) => same numbers"
+        assert not np.array_equal(na, nc)
+        x = na.reshape(-1, 33)
+        n = x.shape[0]
+        assert abs(x.mean()) < 5 / np.sqrt(x.size)
+        assert abs(x.var() - 1) < 5 * np.sqrt(2 / x.size)
+        assert abs((x ** 4).mean() - 3) < 5 * np.sqrt(96 / x.size)
+        assert np.abs(x).max() < 6.8
+        cov = (x.T @ x) / n
+        assert np.abs(cov - np.eye(33)).max() < 6 / np.sqrt(n), "draws of one cell are uncorrelated"
+        # neighbouring cells and consecutive steps are uncorrelated
+        assert abs((na[:, :, 1:, 0] * na[:, :, :-1, 0]).mean()) < 5 / np.sqrt(n)
+        a.step(1)
+        n1 = a.normals()
+        assert abs((n1 * na).mean()) < 5 / np.sqrt(na.size)
+        # per-draw KS-like check on the CDF at a few points
+        from math import erf, sqrt
+        for q in (-2.0, -1.0, 0.0, 0.5, 1.5):
+            want = 0.5 * (1 + erf(q / sqrt(2)))
+            assert abs((x < q).mean() - want) < 5 * np.sqrt(want * (1 - want) / x.size)
+
+
+def test_fused_and_twopass_agree(bflbm):
+    shape = (40, 24, 36)
+    prm = dict(kBT=1e-5, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, tau_f=0.7, tau_g=0.55)
+    with make_lattice(bflbm, shape, prm, "fused") as A, make_lattice(bflbm, shape, prm, "twopass") as B:
+        A.init_droplet(0.25)
+        B.init_droplet(0.25)
+        A.step(20)
+        B.step(20)
+        assert_hydro_close(A.hydrovars(), B.hydrovars(), 1e-11, "fused vs two-pass, 20 fluctuating steps")
+
+
+@pytest.mark.parametrize("lz", [2, 3, 5, 16])
+def test_fused_result_independent_of_brick_height_to_rounding(bflbm, lz):
+    shape = (33, 17, 21)  # partial bricks in every direction
+    prm = dict(kBT=0.0, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0)
+    with make_lattice(bflbm, shape, prm, "fused", lz=lz) as A, make_lattice(bflbm, shape, prm, "twopass") as B:
+        A.init_droplet(0.3)
+        B.init_droplet(0.3)
+        A.step(7)
+        B.step(7)
+        assert_hydro_close(A.hydrovars(), B.hydrovars(), 1e-12, f"lz={lz}")
+
+
+def test_error_behaviour(bflbm):
+    with pytest.raises(bflbm.BflbmError):
+        bflbm.Lattice(8, params=bflbm.Params(alpha1=0.1))
+    with pytest.raises(bflbm.BflbmError):
+        bflbm.Lattice(8, params=bflbm.Params(tau_f=0.0))
+    with bflbm.Lattice(8) as lat:
+        with pytest.raises(bflbm.BflbmError, match="before init"):
+            lat.step(1)
+        lat.init_mixture()
+        assert lat.check_nan() == 0
+        f, g = lat.populations()
+        f[:] = np.nan
+        lat.init_from_populations(f, g)
+        with pytest.raises(bflbm.BflbmError, match="non-finite"):
+            lat.check_nan()
+
+
+def test_center_of_mass_and_mass(bflbm, oracle_mod):
+    shape = (16, 12, 20)
+    prm = dict(kBT=0.0, alpha0=1.5, kappa=0.5, rho_lo=0.1, rho_hi=2.0)
+    O = oracle_mod.PortOracle(*shape)
+    O.set_params(**prm)
+    O.init_droplet(0.3)
+    rho = O.hydrovars_bar()[0]
+    z, y, x = np.meshgrid(np.arange(shape[2]), np.arange(shape[1]), np.arange(shape[0]), indexing="ij")
+    com = np.array([(rho * x).sum(), (rho * y).sum(), (rho * z).sum()]) / rho.sum()
+    with make_lattice(bflbm, shape, prm) as lat:
+        lat.init_droplet(0.3)
+        c, sums = lat.center_of_mass()
+        assert np.allclose(c, com, rtol=1e-12)
+        assert abs(sums[0] - rho.sum()) < 1e-12 * rho.sum()
