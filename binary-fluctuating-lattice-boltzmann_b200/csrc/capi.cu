@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <new>
@@ -44,7 +45,10 @@ struct bflbm_lattice {
   int device = 0;
   bool whole_box = true;
   bool initialized = false;
-  int algo = 0;  // 0 fused, 1 two-pass
+  int algo = 0;  // 0 fused (two threads per cell), 1 two-pass, 2 fused (one thread per cell)
+  int lz_request = 0;
+  int cta_threads = 256;  // threads per CTA of the fused kernel (BFLBM_CTA_THREADS=128|256)
+  bool prefetch = false;  // L2 prefetch of the next plane in the fused kernel (BFLBM_PREFETCH=1)
   long long step = 0;
   long long launches = 0;
   size_t bytes = 0;
@@ -84,6 +88,24 @@ struct bflbm_lattice {
 namespace {
 
 int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+template <int NT>
+cudaError_t set_fused_smem_nt(int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(k_step_fused<true, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused<true, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused<false, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused<false, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return e;
+}
+cudaError_t set_fused_smem(const BrickGrid& B) {
+  if (B.tx * B.ty == 128 && B.tx <= 16) {  // species-split kernel (its smem fits the default limit, set anyway)
+    cudaError_t e = cudaFuncSetAttribute(k_step_fused2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused2_smem_bytes(B));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused2_smem_bytes(B));
+    return e;
+  }
+  const int bytes = (int)fused_smem_bytes(B);
+  return B.tx * B.ty == 128 ? set_fused_smem_nt<128>(bytes) : set_fused_smem_nt<256>(bytes);
+}
 
 inline void mark(bflbm_lattice* h, int i) {
   if (h->profiling) cudaEventRecord(h->ev[i], h->stream);
@@ -287,8 +309,19 @@ int fold_local(bflbm_lattice* h) {
 template <bool NOISE>
 int launch_fused(bflbm_lattice* h) {
   const BrickGrid& B = h->B;
+  if (h->algo == 0) {
+    dim3 grid(B.bx, B.by, B.bz);
+    k_step_fused2<NOISE><<<grid, 256, fused2_smem_bytes(B), h->stream>>>(h->G, B, h->dp, h->step, h->X[h->cur], h->X[1 - h->cur], h->R, h->E);
+    ++h->launches;
+    CU(cudaGetLastError());
+    return 0;
+  }
   dim3 grid(B.bx, B.by, B.bz), block(B.tx, B.ty);
-  k_step_fused<NOISE><<<grid, block, fused_smem_bytes(B), h->stream>>>(h->G, B, h->dp, h->step, h->X[h->cur], h->X[1 - h->cur], h->R, h->E);
+#define BFLBM_LAUNCH_FUSED(PF, NT) \
+  k_step_fused<NOISE, PF, NT><<<grid, block, fused_smem_bytes(B), h->stream>>>(h->G, B, h->dp, h->step, h->X[h->cur], h->X[1 - h->cur], h->R, h->E)
+  if (B.tx * B.ty == 128) { if (h->prefetch) BFLBM_LAUNCH_FUSED(true, 128); else BFLBM_LAUNCH_FUSED(false, 128); }
+  else                    { if (h->prefetch) BFLBM_LAUNCH_FUSED(true, 256); else BFLBM_LAUNCH_FUSED(false, 256); }
+#undef BFLBM_LAUNCH_FUSED
   ++h->launches;
   CU(cudaGetLastError());
   return 0;
@@ -333,6 +366,9 @@ int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, 
   if (rc) return rc;
   if (nx < 1 || ny < 1 || nz_global < 2 || nzl < 2 || z0 < 0 || z0 + nzl > nz_global)
     return fail(BFLBM_ERR_ARG, "bad lattice size nx=%d ny=%d nz=%d z0=%d nz_local=%d (need nx,ny >= 1, nz_local >= 2)", nx, ny, nz_global, z0, nzl);
+  if ((double)(nzl + 2) * nx * ny * 8.0 >= 4294967296.0)
+    return fail(BFLBM_ERR_ARG, "slab too large: (nz_local+2)*nx*ny*8 B must stay below 4 GiB per component (32-bit in-component offsets); "
+                               "use more slabs");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(BFLBM_ERR_CUDA, "no CUDA device available: this library has no CPU path");
@@ -362,7 +398,11 @@ int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, 
   TRY(dev_alloc(h, &h->X[0], (size_t)(2 * Q) * G.comp));
   TRY(dev_alloc(h, &h->X[1], (size_t)(2 * Q) * G.comp));
   TRY(dev_alloc(h, &h->R, (size_t)G.comp));
-  h->B = make_brick_grid(G);
+  {
+    const char* nt = getenv("BFLBM_CTA_THREADS");
+    h->cta_threads = (nt && atoi(nt) == 128) ? 128 : 256;
+  }
+  h->B = make_brick_grid(G, 0, 128, 16);  // default algorithm: species-split fused kernel, 16x8 cells per CTA plane
   TRY(dev_alloc(h, &h->E, brick_doubles2(h->B)));
   h->halo_doubles = (size_t)14 * G.plane;
   for (int s = 0; s < 2; ++s) {
@@ -373,8 +413,9 @@ int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, 
   TRY(dev_alloc(h, &h->diag_partial, h->diag_blocks * 5));
   TRY(dev_alloc(h, &h->diag_count, (size_t)1));
   {
-    cudaError_t e = cudaFuncSetAttribute(k_step_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes(h->B));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes(h->B));
+    const char* pf = getenv("BFLBM_PREFETCH");
+    h->prefetch = pf && pf[0] == '1';
+    cudaError_t e = set_fused_smem(h->B);
     if (e != cudaSuccess) { bflbm_destroy(h); return fail(BFLBM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
   }
 #undef TRY
@@ -519,19 +560,20 @@ int bflbm_set_stream(bflbm_lattice* h, void* s) {
 }
 int bflbm_set_algorithm(bflbm_lattice* h, int algo) {
   CHECK_H(h);
-  if (algo != 0 && algo != 1) return fail(BFLBM_ERR_ARG, "algorithm must be 0 (fused) or 1 (two-pass)");
+  if (algo < 0 || algo > 2) return fail(BFLBM_ERR_ARG, "algorithm must be 0 (fused), 1 (two-pass) or 2 (fused, one thread per cell)");
   if (algo == 1 && !h->whole_box) return fail(BFLBM_ERR_ARG, "the two-pass algorithm supports whole-box lattices only");
   h->algo = algo;
-  return 0;
+  return bflbm_set_tiling(h, h->lz_request);  // the brick shape depends on the kernel
 }
 
 int bflbm_set_tiling(bflbm_lattice* h, int brick_lz) {
   CHECK_H(h);
   if (brick_lz < 0) return fail(BFLBM_ERR_ARG, "brick height must be >= 0");
+  h->lz_request = brick_lz;
   int rc = set_device(h);
   if (rc) return rc;
   CU(cudaStreamSynchronize(h->stream));
-  const BrickGrid nb = make_brick_grid(h->G, brick_lz);
+  const BrickGrid nb = h->algo == 0 ? make_brick_grid(h->G, brick_lz, 128, 16) : make_brick_grid(h->G, brick_lz, h->cta_threads, 32);
   if (brick_doubles2(nb) != brick_doubles2(h->B)) {
     CU(cudaFree(h->E));
     h->bytes -= brick_doubles2(h->B) * sizeof(double2);
@@ -539,8 +581,7 @@ int bflbm_set_tiling(bflbm_lattice* h, int brick_lz) {
     if ((rc = dev_alloc(h, &h->E, brick_doubles2(nb)))) return rc;
   }
   h->B = nb;
-  CU(cudaFuncSetAttribute(k_step_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes(nb)));
-  CU(cudaFuncSetAttribute(k_step_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes(nb)));
+  CU(set_fused_smem(nb));
   return 0;
 }
 

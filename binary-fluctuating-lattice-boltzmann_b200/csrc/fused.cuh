@@ -28,12 +28,12 @@ struct BrickGrid {
   long long brick;  // pl*(lz+2) : extended box, in double2
 };
 
-inline BrickGrid make_brick_grid(const Geom& G, int lz_request = 0) {
+inline BrickGrid make_brick_grid(const Geom& G, int lz_request = 0, int nthreads = 256, int max_tx = 32) {
   BrickGrid B;
   int tx = 8;
-  while (tx < G.nx && tx < 32) tx <<= 1;
+  while (tx < G.nx && tx < max_tx) tx <<= 1;
   B.tx = tx;
-  B.ty = 256 / tx;
+  B.ty = nthreads / tx;  // nthreads = CELLS per CTA plane
   B.bx = (G.nx + B.tx - 1) / B.tx;
   B.by = (G.ny + B.ty - 1) / B.ty;
   int lz = lz_request;
@@ -52,41 +52,54 @@ inline BrickGrid make_brick_grid(const Geom& G, int lz_request = 0) {
   B.brick = (long long)B.pl * (lz + 2);
   return B;
 }
+inline size_t fused2_smem_bytes(const BrickGrid& B) { return (size_t)6 * B.pl * sizeof(double2); }
 inline size_t brick_doubles2(const BrickGrid& B) { return (size_t)B.brick * B.bx * B.by * B.bz; }
-inline size_t fused_smem_bytes(const BrickGrid& B) { return (size_t)6 * B.pl * sizeof(double2); }
-
-__device__ __forceinline__ double shfl_from_left(double v, int tx, int width) {
-  const double r = __shfl_up_sync(0xffffffffu, v, 1, width);
-  return tx == 0 ? 0. : r;
-}
-__device__ __forceinline__ double shfl_from_right(double v, int tx, int width) {
-  const double r = __shfl_down_sync(0xffffffffu, v, 1, width);
-  return tx == width - 1 ? 0. : r;
-}
+inline size_t fused_smem_bytes(const BrickGrid& B) { return (size_t)6 * B.pl * sizeof(double2) + (size_t)15 * B.tx * B.ty * sizeof(double); }
 
 // x-stage of the density scatter for one species.  p: post-collision populations of this thread's cell.
-// t[g]: what arrives in this thread's column for the 9 (cy,cz) groups; sm[5]/sp[5]: what leaves through the
-// left/right face of the tile (meaningful on lanes tx==0 / tx==width-1), for the 5 groups that have cx != 0.
+// t[g]: what arrives in this thread's column for the 9 (cy,cz) groups (own cell + left neighbour's +x movers
+// + right neighbour's -x movers).  Lanes on the tile faces receive nothing from outside the tile: their adds are
+// predicated off (what leaves through a face is exported separately, see ef/eg in the kernel).
 // group index: 0 (0,0)  1 (+1,0)  2 (-1,0)  3 (0,+1)  4 (0,-1)  5 (+1,+1)  6 (-1,-1)  7 (+1,-1)  8 (-1,+1)
+__device__ __forceinline__ double scatter_x1(double own, double to_right, double to_left, double has_left, double has_right, int width) {
+  const double l = __shfl_up_sync(0xffffffffu, to_right, 1, width);
+  const double r = __shfl_down_sync(0xffffffffu, to_left, 1, width);
+  // has_* are exactly 1.0 or 0.0: the fma is an exact masked add (same rounding as own + l + r)
+  return fma(r, has_right, fma(l, has_left, own));
+}
 __device__ __forceinline__ void scatter_x(const double (&p)[Q], int tx, int width, double (&t)[9]) {
-  t[0] = p[0] + shfl_from_left(p[1], tx, width) + shfl_from_right(p[2], tx, width);
-  t[1] = p[3] + shfl_from_left(p[7], tx, width) + shfl_from_right(p[10], tx, width);
-  t[2] = p[4] + shfl_from_left(p[9], tx, width) + shfl_from_right(p[8], tx, width);
-  t[3] = p[5] + shfl_from_left(p[15], tx, width) + shfl_from_right(p[18], tx, width);
-  t[4] = p[6] + shfl_from_left(p[17], tx, width) + shfl_from_right(p[16], tx, width);
+  const double hl = tx != 0 ? 1. : 0., hr = tx != width - 1 ? 1. : 0.;
+  t[0] = scatter_x1(p[0], p[1], p[2], hl, hr, width);
+  t[1] = scatter_x1(p[3], p[7], p[10], hl, hr, width);
+  t[2] = scatter_x1(p[4], p[9], p[8], hl, hr, width);
+  t[3] = scatter_x1(p[5], p[15], p[18], hl, hr, width);
+  t[4] = scatter_x1(p[6], p[17], p[16], hl, hr, width);
   t[5] = p[11];
   t[6] = p[12];
   t[7] = p[13];
   t[8] = p[14];
 }
 
-template <bool NOISE>
-__global__ void __launch_bounds__(256, 2)
+// 32-bit byte offsets inside one component + one (warp-uniform) 64-bit base per component: the pull addresses
+// cost one integer add per direction instead of a 64-bit multiply-add per load.
+__device__ __forceinline__ double ld_off(const double* __restrict__ base, unsigned byte_off) {
+  return __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + byte_off));
+}
+__device__ __forceinline__ void prefetch_l2(const double* __restrict__ base, unsigned byte_off) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + byte_off));
+}
+__device__ __forceinline__ void st_off(double* __restrict__ base, unsigned byte_off, double v) {
+  *reinterpret_cast<double*>(reinterpret_cast<char*>(base) + byte_off) = v;
+}
+
+template <bool NOISE, bool PREFETCH, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT)
 k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __restrict__ X, double* __restrict__ Xn,
              const double2* __restrict__ R, double2* __restrict__ E) {
   extern __shared__ double2 smem[];
   double2* Rs = smem;             // [3][ey][ex] rolling (rho,phi) planes zl-1, zl, zl+1
   double2* A = smem + 3 * B.pl;   // [3][ey][ex] rolling accumulators of next-step (rho,phi)
+  double* Sg = reinterpret_cast<double*>(smem + 6 * B.pl);  // [15][256] parked moments 4..18 of species g
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * B.tx + tx;
   const int x0 = blockIdx.x * B.tx, y0 = blockIdx.y * B.ty, zb = blockIdx.z * B.lz;
   const int x = x0 + tx, y = y0 + ty;
@@ -97,7 +110,7 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
   // stage one (rho,phi) plane zl (-1..nzl) of the tile + ring into slot s
   auto stage_plane = [&](int zl, int s) {
     const double2* Rp = R + (long long)(zl + 1) * G.plane;
-    for (int idx = tid; idx < B.pl; idx += 256) {
+    for (int idx = tid; idx < B.pl; idx += NT) {
       const int ey = idx / B.ex, exx = idx - ey * B.ex;
       int gx = (x0 - 1 + exx) % G.nx, gy = (y0 - 1 + ey) % G.ny;
       gx = gx < 0 ? gx + G.nx : gx;
@@ -105,7 +118,7 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
       Rs[s * B.pl + idx] = __ldg(Rp + (long long)gy * G.nx + gx);
     }
   };
-  for (int idx = tid; idx < 3 * B.pl; idx += 256) A[idx] = make_double2(0., 0.);
+  for (int idx = tid; idx < 3 * B.pl; idx += NT) A[idx] = make_double2(0., 0.);
   stage_plane(zb - 1, 0);
   stage_plane(zb, 1);
   stage_plane(zb + 1, 2);
@@ -118,56 +131,91 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
     const int s_m = k % 3, s_0 = (k + 1) % 3, s_p = (k + 2) % 3;
     double tf[9], tg[9];
     double ef[5], eg[5];  // edge exports (left face on lane 0, right face on lane tx-1)
-#pragma unroll
-    for (int j = 0; j < 5; ++j) ef[j] = eg[j] = 0.;
+    const bool left = tx == 0;
     {
       double mf[Q], mg[Q];
-      long long c = 0;
+      unsigned c = 0;  // byte offset of this cell inside a component
+      CollideCtx C;
+      NoiseKey nk;
       if (active) {
-        const CellIdx I = cell_idx(G, x, y, zl);
-        c = I.zpl[1] + I.yrow[1] + x;
+        // gradients first (LBM_binary.H:134-150): only 6 doubles stay live across the population loads
+        double grho[3], gphi[3];
+        {
+          double nr[Q], np[Q];
+          nr[0] = np[0] = 0.;
+          const int sl[3] = {s_m, s_0, s_p};
+#pragma unroll
+          for (int i = 1; i < Q; ++i) {
+            const double2 v = Rs[sl[1 + cz(i)] * B.pl + cell + cy(i) * B.ex + cx(i)];
+            nr[i] = v.x;
+            np[i] = v.y;
+          }
+          gradient19(nr, grho);
+          gradient19(np, gphi);
+        }
+        // byte offsets of the 19 pull sources (x - c_i) inside a component; < 4 GiB is checked at creation
+        unsigned off[Q];
+        {
+          const unsigned xs[3] = {(unsigned)(x == 0 ? G.nx - 1 : x - 1), (unsigned)x, (unsigned)(x == G.nx - 1 ? 0 : x + 1)};
+          const unsigned yr[3] = {(unsigned)(y == 0 ? G.ny - 1 : y - 1) * (unsigned)G.nx, (unsigned)y * (unsigned)G.nx,
+                                  (unsigned)(y == G.ny - 1 ? 0 : y + 1) * (unsigned)G.nx};
+          const unsigned pl = (unsigned)G.plane;
+          const unsigned zp[3] = {(unsigned)zl * pl, (unsigned)(zl + 1) * pl, (unsigned)(zl + 2) * pl};
+#pragma unroll
+          for (int i = 0; i < Q; ++i) off[i] = (zp[1 - cz(i)] + yr[1 - cy(i)] + xs[1 - cx(i)]) * 8u;
+          c = off[0];
+        }
+        if (PREFETCH && (tx & 15) == 0 && k + 1 < vz) {
+          // next plane of this column into L2 (one request per 128 B line) while this plane computes
+          const unsigned nxt = c + (unsigned)G.plane * 8u;
+#pragma unroll
+          for (int i = 0; i < 2 * Q; ++i) prefetch_l2(X + (long long)i * G.comp, nxt);
+        }
         {
           double f[Q];
-          pull19(X, G, I, f);
-          moments(f, mf);
-          pull19(X + (long long)Q * G.comp, G, I, f);
-          moments(f, mg);
-        }
-        // gradients from the staged neighbourhood (LBM_binary.H:134-150)
-        double nr[Q], np[Q], grho[3], gphi[3];
-        nr[0] = np[0] = 0.;
-        const int sl[3] = {s_m, s_0, s_p};
+          // species g first: its non-conserved moments wait in shared memory while species f is processed
 #pragma unroll
-        for (int i = 1; i < Q; ++i) {
-          const double2 v = Rs[sl[1 + cz(i)] * B.pl + cell + cy(i) * B.ex + cx(i)];
-          nr[i] = v.x;
-          np[i] = v.y;
+          for (int i = 0; i < Q; ++i) f[i] = ld_off(X + (long long)(Q + i) * G.comp, off[i]);
+          moments(f, mg);
+#pragma unroll
+          for (int a = 4; a < Q; ++a) Sg[(a - 4) * NT + tid] = mg[a];
+#pragma unroll
+          for (int i = 0; i < Q; ++i) f[i] = ld_off(X + (long long)i * G.comp, off[i]);
+          moments(f, mf);
         }
-        gradient19(nr, grho);
-        gradient19(np, gphi);
-        const NoiseKey nk = make_noise_key(P.seed, (unsigned long long)cell_global(G, x, y, zl), step);
-        collide_cell<NOISE>(P, grho, gphi, nk, mf, mg);
+        nk = make_noise_key(P.seed, (unsigned long long)cell_global(G, x, y, zl), step);
+        collide_prepare<NOISE>(P, grho, gphi, nk, mf, mg, C);
+        collide_species<NOISE, 0>(P, nk, C, mf);
       } else {
 #pragma unroll
-        for (int i = 0; i < Q; ++i) mf[i] = mg[i] = 0.;
+        for (int i = 0; i < Q; ++i) mf[i] = 0.;
       }
       double p[Q];
       populations(mf, p);
       if (active) {
 #pragma unroll
-        for (int i = 0; i < Q; ++i) Xn[(long long)i * G.comp + c] = p[i];
+        for (int i = 0; i < Q; ++i) st_off(Xn + (long long)i * G.comp, c, p[i]);
       }
       scatter_x(p, tx, B.tx, tf);
-      if (tx == 0)        { ef[0] = p[2]; ef[1] = p[10]; ef[2] = p[8]; ef[3] = p[18]; ef[4] = p[16]; }
-      if (tx == B.tx - 1) { ef[0] = p[1]; ef[1] = p[7];  ef[2] = p[9]; ef[3] = p[15]; ef[4] = p[17]; }
+      // what leaves through the left face (lane 0) / right face (lane tx-1); unused on the other lanes
+      ef[0] = left ? p[2] : p[1]; ef[1] = left ? p[10] : p[7]; ef[2] = left ? p[8] : p[9];
+      ef[3] = left ? p[18] : p[15]; ef[4] = left ? p[16] : p[17];
+      if (active) {
+#pragma unroll
+        for (int a = 4; a < Q; ++a) mg[a] = Sg[(a - 4) * NT + tid];
+        collide_species<NOISE, 1>(P, nk, C, mg);
+      } else {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) mg[i] = 0.;
+      }
       populations(mg, p);
       if (active) {
 #pragma unroll
-        for (int i = 0; i < Q; ++i) Xn[(long long)(Q + i) * G.comp + c] = p[i];
+        for (int i = 0; i < Q; ++i) st_off(Xn + (long long)(Q + i) * G.comp, c, p[i]);
       }
       scatter_x(p, tx, B.tx, tg);
-      if (tx == 0)        { eg[0] = p[2]; eg[1] = p[10]; eg[2] = p[8]; eg[3] = p[18]; eg[4] = p[16]; }
-      if (tx == B.tx - 1) { eg[0] = p[1]; eg[1] = p[7];  eg[2] = p[9]; eg[3] = p[15]; eg[4] = p[17]; }
+      eg[0] = left ? p[2] : p[1]; eg[1] = left ? p[10] : p[7]; eg[2] = left ? p[8] : p[9];
+      eg[3] = left ? p[18] : p[15]; eg[4] = left ? p[16] : p[17];
     }
     // a tile narrower than two lanes would need both faces on one lane; tx >= 8 always
     const bool edge = (tx == 0) || (tx == B.tx - 1);
@@ -204,14 +252,206 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
     if (edge) add(s_0, ecell - B.ex, ef[2], eg[2]);
     __syncthreads();
     // plane zl-1 has received everything this brick can give it: write it out (extended plane k) and recycle
-    for (int idx = tid; idx < B.pl; idx += 256) {
+    for (int idx = tid; idx < B.pl; idx += NT) {
       Eb[(long long)k * B.pl + idx] = A[s_m * B.pl + idx];
       A[s_m * B.pl + idx] = make_double2(0., 0.);
     }
   }
   __syncthreads();
   // the two planes still in flight: zl = zb+vz-1 (extended plane vz) and the top shell (vz+1)
-  for (int idx = tid; idx < B.pl; idx += 256) {
+  for (int idx = tid; idx < B.pl; idx += NT) {
+    Eb[(long long)vz * B.pl + idx] = A[(vz % 3) * B.pl + idx];
+    Eb[(long long)(vz + 1) * B.pl + idx] = A[((vz + 1) % 3) * B.pl + idx];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Species-split variant of the fused step: TWO threads per cell, lane l (l < 16) handles species f and lane
+// l + 16 species g of the same cell (a warp = 16 consecutive cells x 2 species).  Each thread carries 19
+// instead of 38 populations, so the kernel fits 3 CTAs (24 warps) per SM instead of 16 warps, and the
+// per-warp critical path between barriers is half as long: the collision is latency/issue bound
+// (profiles/r1_*), not DRAM bound, and more resident warps is what it needs.
+// The code is species-uniform: the species enters only as data (base pointers, rate, sign of the momentum
+// noise, Philox block offset), so the two half-warps never diverge.  What each thread needs from the other
+// species (density, momentum, acceleration, real velocity) crosses with shfl.xor 16.
+
+// everything the relaxation of species s needs: own real velocity u, barycentric velocity vb, momentum noise xi
+template <bool NOISE>
+__device__ __forceinline__ void pair_hydro(const DevParams& P, int s, double dens_s, const double (&j_s)[3], const double (&a_s)[3],
+                                           const float (&n3)[3], double (&u_s)[3], double (&vb)[3], double (&xi_s)[3]) {
+  const unsigned full = 0xffffffffu;
+  const double dens_o = __shfl_xor_sync(full, dens_s, 16);
+  const bool has_s = fabs(dens_s) > (double)FLT_EPSILON;
+  const double inv_s = has_s ? 1. / dens_s : 0.;
+  const double inv_o = __shfl_xor_sync(full, inv_s, 16);
+  const double inv_tot = 1. / (dens_s + dens_o);  // unguarded like the reference; a+b is the same in both lanes
+  const double fric_s = s ? P.fric_g : P.fric_f;
+  double amp = 0.;
+  if (NOISE) amp = sqrt(P.amp_j * fabs(dens_s * dens_o * inv_tot));
+  const double sign = s ? -1. : 1.;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double j_o = __shfl_xor_sync(full, j_s[k], 16), a_o = __shfl_xor_sync(full, a_s[k], 16);
+    const double ub_s = j_s[k] * inv_s, ub_o = j_o * inv_o;
+    xi_s[k] = NOISE ? sign * (amp * (double)n3[k]) : 0.;
+    const double d = (ub_s - ub_o) + 0.5 * (a_s[k] - a_o);
+    u_s[k] = ub_s + 0.5 * a_s[k] - fric_s * dens_o * inv_tot * d + 0.5 * (xi_s[k] * inv_s);
+    const double u_o = __shfl_xor_sync(full, u_s[k], 16);
+    // (rho u_f + phi u_g)/(rho+phi), LBM_binary.H:471; no fma contraction so that both lanes get the same bits
+    vb[k] = __dmul_rn(__dadd_rn(__dmul_rn(dens_s, u_s[k]), __dmul_rn(dens_o, u_o)), inv_tot);
+  }
+}
+
+template <bool NOISE>
+__global__ void __launch_bounds__(256, 3)
+k_step_fused2(Geom G, BrickGrid B, DevParams P, long long step, const double* __restrict__ X, double* __restrict__ Xn,
+              const double2* __restrict__ R, double2* __restrict__ E) {
+  constexpr int NT = 256;
+  extern __shared__ double2 smem[];
+  double2* Rs = smem;             // [3][ey][ex] rolling (rho,phi) planes zl-1, zl, zl+1
+  double2* A = smem + 3 * B.pl;   // [3][ey][ex] rolling accumulators of next-step (rho,phi)
+  double* Ad = reinterpret_cast<double*>(A);
+  const double* Rd = reinterpret_cast<const double*>(Rs);
+  const int tid = threadIdx.x, lane = tid & 31, s = lane >> 4;
+  const int cidx = (tid >> 5) * 16 + (lane & 15);  // cell of the tile (tx*ty = 128 cells)
+  const int tx = cidx % B.tx, ty = cidx / B.tx;
+  const int x0 = blockIdx.x * B.tx, y0 = blockIdx.y * B.ty, zb = blockIdx.z * B.lz;
+  const int x = x0 + tx, y = y0 + ty;
+  const bool active = x < G.nx && y < G.ny;
+  const int vz = min(B.lz, G.nzl - zb);
+  double2* Eb = E + (((long long)blockIdx.z * B.by + blockIdx.y) * B.bx + blockIdx.x) * B.brick;
+  const double* __restrict__ Xs = X + (long long)(s * Q) * G.comp;
+  double* __restrict__ Xns = Xn + (long long)(s * Q) * G.comp;
+
+  auto stage_plane = [&](int zl, int slot) {
+    const double2* Rp = R + (long long)(zl + 1) * G.plane;
+    for (int idx = tid; idx < B.pl; idx += NT) {
+      const int ey = idx / B.ex, exx = idx - ey * B.ex;
+      int gx = (x0 - 1 + exx) % G.nx, gy = (y0 - 1 + ey) % G.ny;
+      gx = gx < 0 ? gx + G.nx : gx;
+      gy = gy < 0 ? gy + G.ny : gy;
+      Rs[slot * B.pl + idx] = __ldg(Rp + (long long)gy * G.nx + gx);
+    }
+  };
+  for (int idx = tid; idx < 3 * B.pl; idx += NT) A[idx] = make_double2(0., 0.);
+  stage_plane(zb - 1, 0);
+  stage_plane(zb, 1);
+  stage_plane(zb + 1, 2);
+  __syncthreads();
+
+  // in-component byte offsets of the in-plane parts of the 19 pull sources (plane part added per plane)
+  const unsigned xs[3] = {(unsigned)(x == 0 ? G.nx - 1 : x - 1), (unsigned)min(x, G.nx - 1), (unsigned)(x >= G.nx - 1 ? 0 : x + 1)};
+  const int yc = min(y, G.ny - 1);
+  const unsigned yr[3] = {(unsigned)(yc == 0 ? G.ny - 1 : yc - 1) * (unsigned)G.nx, (unsigned)yc * (unsigned)G.nx,
+                          (unsigned)(yc == G.ny - 1 ? 0 : yc + 1) * (unsigned)G.nx};
+  const int cell = (ty + 1) * B.ex + (tx + 1);  // this thread's cell in an extended plane
+  const bool left = tx == 0, edge = left || tx == B.tx - 1;
+  const int ecell = (ty + 1) * B.ex + (left ? 0 : B.tx + 1);
+  const double rate = s ? P.rate_g : P.rate_f;
+
+  for (int k = 0; k < vz; ++k) {
+    const int zl = zb + k;
+    const int s_m = k % 3, s_0 = (k + 1) % 3, s_p = (k + 2) % 3;  // slot of plane zl + d : (k + 1 + d) % 3
+    double t[9], e[5];
+    {
+      // acceleration of this species from the gradient of the OTHER species' density (LBM_binary.H:134-150, 254-255)
+      double go[3];
+      {
+        double n[Q];
+        n[0] = 0.;
+        const int sl[3] = {s_m, s_0, s_p};
+#pragma unroll
+        for (int i = 1; i < Q; ++i) n[i] = Rd[2 * (sl[1 + cz(i)] * B.pl + cell + cy(i) * B.ex + cx(i)) + (1 - s)];
+        gradient19(n, go);
+      }
+      const unsigned pl8 = (unsigned)G.plane * 8u;
+      const unsigned zp[3] = {(unsigned)zl * pl8, (unsigned)(zl + 1) * pl8, (unsigned)(zl + 2) * pl8};
+      const unsigned c = zp[1] + (yr[1] + xs[1]) * 8u;
+      double m[Q];
+      {
+        double f[Q];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+          const unsigned off = zp[1 - cz(i)] + (yr[1 - cy(i)] + xs[1 - cx(i)]) * 8u;
+          f[i] = active ? ld_off(Xs + (long long)i * G.comp, off) : 0.;
+        }
+        moments(f, m);
+      }
+      const bool has_s = fabs(m[0]) > (double)FLT_EPSILON;
+      double a_s[3], u_s[3], vb[3], xi_s[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) a_s[d] = has_s ? P.acc_coef * go[d] : 0.;
+      NoiseKey nk;
+      float n0[4] = {0.f, 0.f, 0.f, 0.f};
+      if (NOISE) {
+        nk = make_noise_key(P.seed, (unsigned long long)cell_global(G, x, y, zl), step);
+        normals4(nk, 0, n0);
+      }
+      {
+        const double j_s[3] = {m[1], m[2], m[3]};
+        const float n3[3] = {n0[0], n0[1], n0[2]};
+        pair_hydro<NOISE>(P, s, m[0], j_s, a_s, n3, u_s, vb, xi_s);
+      }
+      relax_species(rate, P.force_pf, m[0], vb, u_s, a_s, m);
+      if (NOISE) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) m[1 + d] += xi_s[d];
+        const double sa = sqrt(P.amp_s * fabs(m[0]));
+        float nb[4];
+#pragma unroll
+        for (int a = 4; a < Q; ++a) {
+          if (((a - 4) & 3) == 0) normals4(nk, 1 + 4 * s + ((a - 4) >> 2), nb);  // = mode_index(s, a) >> 2
+          m[a] += (sqrt_bnorm(a) * sa) * (double)nb[(a - 4) & 3];
+        }
+      }
+      double p[Q];
+      populations(m, p);
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) st_off(Xns + (long long)i * G.comp, c, p[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) p[i] = 0.;
+      }
+      scatter_x(p, tx, B.tx, t);
+      // what leaves through the left face (lane 0) / right face (lane tx-1); unused on the other lanes
+      e[0] = left ? p[2] : p[1]; e[1] = left ? p[10] : p[7]; e[2] = left ? p[8] : p[9];
+      e[3] = left ? p[18] : p[15]; e[4] = left ? p[16] : p[17];
+    }
+
+    __syncthreads();  // S0: everyone is done reading Rs slot s_m (plane zl-1) and the last write-out is finished
+    if (zl + 2 <= G.nzl) stage_plane(zl + 2, s_m);
+    auto add = [&](int slot, int at, double v) { Ad[2 * (slot * B.pl + at) + s] += v; };
+    // phase cy = 0 : own row.  groups 0 (cz 0), 3 (cz +1), 4 (cz -1)
+    add(s_0, cell, t[0]);
+    add(s_p, cell, t[3]);
+    add(s_m, cell, t[4]);
+    if (edge) {
+      add(s_0, ecell, e[0]);
+      add(s_p, ecell, e[3]);
+      add(s_m, ecell, e[4]);
+    }
+    __syncthreads();
+    // phase cy = +1 : row above.  groups 1 (cz 0), 5 (cz +1), 7 (cz -1)
+    add(s_0, cell + B.ex, t[1]);
+    add(s_p, cell + B.ex, t[5]);
+    add(s_m, cell + B.ex, t[7]);
+    if (edge) add(s_0, ecell + B.ex, e[1]);
+    __syncthreads();
+    // phase cy = -1 : row below.  groups 2 (cz 0), 8 (cz +1), 6 (cz -1)
+    add(s_0, cell - B.ex, t[2]);
+    add(s_p, cell - B.ex, t[8]);
+    add(s_m, cell - B.ex, t[6]);
+    if (edge) add(s_0, ecell - B.ex, e[2]);
+    __syncthreads();
+    // plane zl-1 has received everything this brick can give it: write it out (extended plane k) and recycle
+    for (int idx = tid; idx < B.pl; idx += NT) {
+      Eb[(long long)k * B.pl + idx] = A[s_m * B.pl + idx];
+      A[s_m * B.pl + idx] = make_double2(0., 0.);
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < B.pl; idx += NT) {
     Eb[(long long)vz * B.pl + idx] = A[(vz % 3) * B.pl + idx];
     Eb[(long long)(vz + 1) * B.pl + idx] = A[((vz + 1) % 3) * B.pl + idx];
   }

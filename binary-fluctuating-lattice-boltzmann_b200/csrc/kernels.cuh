@@ -104,12 +104,15 @@ __global__ void __launch_bounds__(256) k_step_twopass(Geom G, DevParams P, long 
   double grho[3], gphi[3];
   density_gradients(R, I, grho, gphi);
   const NoiseKey nk = make_noise_key(P.seed, (unsigned long long)cell_global(G, x, y, zl), step);
-  collide_cell<NOISE>(P, grho, gphi, nk, mf, mg);
+  CollideCtx C;
+  collide_prepare<NOISE>(P, grho, gphi, nk, mf, mg, C);
   const long long c = I.zpl[1] + I.yrow[1] + x;
   double f[Q];
+  collide_species<NOISE, 0>(P, nk, C, mf);
   populations(mf, f);
 #pragma unroll
   for (int i = 0; i < Q; ++i) Xn[(long long)i * G.comp + c] = f[i];
+  collide_species<NOISE, 1>(P, nk, C, mg);
   populations(mg, f);
 #pragma unroll
   for (int i = 0; i < Q; ++i) Xn[(long long)(Q + i) * G.comp + c] = f[i];

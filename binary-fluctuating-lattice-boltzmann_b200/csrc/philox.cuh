@@ -20,33 +20,37 @@ namespace bflbm {
 __host__ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 #pragma unroll
   for (int r = 0; r < BFLBM_PHILOX_ROUNDS; ++r) {
-#ifdef __CUDA_ARCH__
-    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), hi1 = __umulhi(0xCD9E8D57u, ctr.z);
-#else
-    const uint32_t hi0 = (uint32_t)(((uint64_t)0xD2511F53u * ctr.x) >> 32), hi1 = (uint32_t)(((uint64_t)0xCD9E8D57u * ctr.z) >> 32);
-#endif
-    const uint32_t lo0 = 0xD2511F53u * ctr.x, lo1 = 0xCD9E8D57u * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    const uint64_t p0 = (uint64_t)0xD2511F53u * ctr.x, p1 = (uint64_t)0xCD9E8D57u * ctr.z;  // one IMAD.WIDE each
+    ctr = make_uint4((uint32_t)(p1 >> 32) ^ ctr.y ^ key.x, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ ctr.w ^ key.y, (uint32_t)p0);
     key.x += 0x9E3779B9u;
     key.y += 0xBB67AE85u;
   }
   return ctr;
 }
 
+// MUFU fast paths, flush-to-zero, no denormal/IEEE fix-up code around them
+__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_sin(float x) { float r; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_cos(float x) { float r; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // two uniforms -> two independent standard normals
 __device__ __forceinline__ void box_muller(uint32_t u0, uint32_t u1, float& n0, float& n1) {
   // U in (0,1]: (u0 + 0.5) / 2^32, tail down to 2^-33 (|n| <= 6.76)
   const float U = fmaf((float)u0, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  const float r = sqrtf(-1.3862943611198906f * __log2f(U));           // sqrt(-2 ln U), ln U = ln2 * lg2 U
+  const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(U));     // sqrt(-2 ln U), ln U = ln2 * lg2 U
   const float th = (float)(int32_t)u1 * 1.4629180792671596e-9f;      // pi * 2^-31 * s32  in [-pi, pi)
-  float s, c;
-  __sincosf(th, &s, &c);
-  n0 = r * c;
-  n1 = r * s;
+  n0 = r * fast_cos(th);
+  n1 = r * fast_sin(th);
 }
 
 // Philox counter layout: {cell_lo, cell_hi, step_lo, (step_hi & 0xffffff) | block << 24}, key = seed.
-// Block j yields draws 4j .. 4j+3.
+// Block j yields the internal normals 4j .. 4j+3.  Internal order (species-symmetric, so that the two threads
+// that share a cell in the fused kernel run identical code on different blocks):
+//   0..2    momentum modes a = 1..3 (species f gets +xi, species g gets -xi); 3 unused
+//   4..18   species f, modes a = 4..18 (blocks 1-4);  19 unused
+//   20..34  species g, modes a = 4..18 (blocks 5-8);  35 unused
+// draw_index() maps the reference's draw order (a = 4..18: f then g, interleaved) onto it.
 struct NoiseKey {
   uint2 key;
   uint32_t cell_lo, cell_hi, step_lo, step_hi;
@@ -60,6 +64,11 @@ __device__ __forceinline__ NoiseKey make_noise_key(unsigned long long seed, unsi
   k.step_hi = (uint32_t)((unsigned long long)step >> 32) & 0x00ffffffu;
   return k;
 }
+// internal index of the normal that drives mode a (4..18) of species s (0 = f, 1 = g)
+__host__ __device__ constexpr int mode_index(int s, int a) { return 4 + 16 * s + (a - 4); }
+// reference draw d (0..32, LBM_binary.H:115-127) -> internal normal index
+__host__ __device__ constexpr int draw_index(int d) { return d < 3 ? d : mode_index((d - 3) & 1, 4 + ((d - 3) >> 1)); }
+
 __device__ __forceinline__ void normals4(const NoiseKey& k, int block, float (&n)[4]) {
   const uint4 r = philox4x32(make_uint4(k.cell_lo, k.cell_hi, k.step_lo, k.step_hi | ((uint32_t)block << 24)), k.key);
   box_muller(r.x, r.y, n[0], n[1]);

@@ -91,49 +91,59 @@ __device__ __forceinline__ void relax_species(double rate, double pf, double D, 
   for (int k = 10; k < Q; ++k) m[k] = keep * m[k];
 }
 
-// full collision of one cell in moment space; mf, mg in: moments of the post-stream populations,
-// out: post-collision moments.  Returns the hydro fields used (for the observers).
+// Collision of one cell in moment space, split in three so that the caller can finish species f (inverse
+// transform, store) before touching species g:
+//   collide_prepare : hydro fields + barycentric velocity (needs the conserved moments of both species)
+//   collide_species : relaxation + forcing + noise of one species, in place
+struct CollideCtx {
+  CellHydro H;
+  double vb[3];
+};
+
 template <bool NOISE>
-__device__ __forceinline__ void collide_cell(const DevParams& P, const double (&grad_rho)[3], const double (&grad_phi)[3],
-                                             const NoiseKey& nk, double (&mf)[Q], double (&mg)[Q]) {
+__device__ __forceinline__ void collide_prepare(const DevParams& P, const double (&grad_rho)[3], const double (&grad_phi)[3],
+                                                const NoiseKey& nk, const double (&mf)[Q], const double (&mg)[Q], CollideCtx& C) {
   float n0[4] = {0.f, 0.f, 0.f, 0.f};
   if (NOISE) normals4(nk, 0, n0);
   const float n3[3] = {n0[0], n0[1], n0[2]};
   const double jf[3] = {mf[1], mf[2], mf[3]}, jg[3] = {mg[1], mg[2], mg[3]};
-  CellHydro H;
-  cell_hydro<NOISE>(P, mf[0], mg[0], jf, jg, grad_rho, grad_phi, n3, H);
-  double vb[3];
+  cell_hydro<NOISE>(P, mf[0], mg[0], jf, jg, grad_rho, grad_phi, n3, C.H);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) vb[k] = (H.rho * H.uf[k] + H.phi * H.ug[k]) * H.inv_tot;  // LBM_binary.H:471
-  relax_species(P.rate_f, P.force_pf, H.rho, vb, H.uf, H.af, mf);
-  relax_species(P.rate_g, P.force_pf, H.phi, vb, H.ug, H.ag, mg);
+  for (int k = 0; k < 3; ++k) C.vb[k] = (C.H.rho * C.H.uf[k] + C.H.phi * C.H.ug[k]) * C.H.inv_tot;  // LBM_binary.H:471
+}
+
+// SPECIES 0 = f (call first), 1 = g
+template <bool NOISE, int SPECIES>
+__device__ __forceinline__ void collide_species(const DevParams& P, const NoiseKey& nk, CollideCtx& C, double (&m)[Q]) {
+  const CellHydro& H = C.H;
+  if (SPECIES == 0) relax_species(P.rate_f, P.force_pf, H.rho, C.vb, H.uf, H.af, m);
+  else              relax_species(P.rate_g, P.force_pf, H.phi, C.vb, H.ug, H.ag, m);
   if (NOISE) {
-    // draws in the reference's order: d = 0..2 momentum (f: +, g: -), then for a = 4..18: f, g
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      mf[1 + k] += H.xi[k];
-      mg[1 + k] -= H.xi[k];
-    }
-    const double sf = sqrt(P.amp_s * fabs(H.rho)), sg = sqrt(P.amp_s * fabs(H.phi));
-    float nb[4] = {n0[0], n0[1], n0[2], n0[3]};
+    for (int k = 0; k < 3; ++k) m[1 + k] += (SPECIES == 0 ? H.xi[k] : -H.xi[k]);
+    const double s = sqrt(P.amp_s * fabs(SPECIES == 0 ? H.rho : H.phi));
+    float nb[4];
 #pragma unroll
-    for (int d = 3; d < 33; ++d) {
-      if ((d & 3) == 0) normals4(nk, d >> 2, nb);
-      const int a = 4 + ((d - 3) >> 1);
-      if (((d - 3) & 1) == 0) mf[a] += (sqrt_bnorm(a) * sf) * (double)nb[d & 3];
-      else                    mg[a] += (sqrt_bnorm(a) * sg) * (double)nb[d & 3];
+    for (int a = 4; a < Q; ++a) {
+      const int j = mode_index(SPECIES, a);
+      if ((j & 3) == 0) normals4(nk, j >> 2, nb);
+      m[a] += (sqrt_bnorm(a) * s) * (double)nb[j & 3];
     }
   }
 }
 
-// the 33 standard normals of a cell in reference draw order (observer / test hook)
+// the 33 standard normals of a cell in REFERENCE draw order (observer / test hook)
 __device__ __forceinline__ void cell_normals(const NoiseKey& nk, float (&n)[36]) {
+  float raw[36];
 #pragma unroll
   for (int b = 0; b < 9; ++b) {
     float t[4];
     normals4(nk, b, t);
-    n[4 * b] = t[0]; n[4 * b + 1] = t[1]; n[4 * b + 2] = t[2]; n[4 * b + 3] = t[3];
+    raw[4 * b] = t[0]; raw[4 * b + 1] = t[1]; raw[4 * b + 2] = t[2]; raw[4 * b + 3] = t[3];
   }
+#pragma unroll
+  for (int d = 0; d < 33; ++d) n[d] = raw[draw_index(d)];
+  n[33] = n[34] = n[35] = 0.f;
 }
 
 }  // namespace bflbm
