@@ -148,7 +148,7 @@ void derive(bflbm_lattice* h) {
   const double A = 2. * (lam - 0.5 * lam * lam);
   d.amp_j = A * p.kBT;
   d.amp_s = A * p.kBT / (1. / 3.);
-  d.seed = p.seed;
+  d.keys = philox_key_schedule(p.seed);
 }
 
 template <class T>

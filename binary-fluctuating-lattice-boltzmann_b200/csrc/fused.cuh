@@ -107,16 +107,24 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
   const int vz = min(B.lz, G.nzl - zb);
   double2* Eb = E + (((long long)blockIdx.z * B.by + blockIdx.y) * B.bx + blockIdx.x) * B.brick;
 
-  // stage one (rho,phi) plane zl (-1..nzl) of the tile + ring into slot s
+  // stage one (rho,phi) plane zl (-1..nzl) of the tile + ring into slot s.  The in-plane source offsets are the
+  // same for every plane: computed once (each thread owns at most STG entries of the extended plane).
+  constexpr int STG = 2;  // pl = (tx+2)(ty+2) <= 2*NT for every tile shape used (tx in 8..32, tx*ty = NT >= 128)
+  int soff[STG];
+#pragma unroll
+  for (int j = 0; j < STG; ++j) {
+    const int idx = tid + j * NT;
+    const int ey = idx / B.ex, exx = idx - ey * B.ex;
+    int gx = (x0 - 1 + exx) % G.nx, gy = (y0 - 1 + ey) % G.ny;
+    gx = gx < 0 ? gx + G.nx : gx;
+    gy = gy < 0 ? gy + G.ny : gy;
+    soff[j] = idx < B.pl ? gy * G.nx + gx : -1;
+  }
   auto stage_plane = [&](int zl, int s) {
     const double2* Rp = R + (long long)(zl + 1) * G.plane;
-    for (int idx = tid; idx < B.pl; idx += NT) {
-      const int ey = idx / B.ex, exx = idx - ey * B.ex;
-      int gx = (x0 - 1 + exx) % G.nx, gy = (y0 - 1 + ey) % G.ny;
-      gx = gx < 0 ? gx + G.nx : gx;
-      gy = gy < 0 ? gy + G.ny : gy;
-      Rs[s * B.pl + idx] = __ldg(Rp + (long long)gy * G.nx + gx);
-    }
+#pragma unroll
+    for (int j = 0; j < STG; ++j)
+      if (soff[j] >= 0) Rs[s * B.pl + tid + j * NT] = __ldg(Rp + soff[j]);
   };
   for (int idx = tid; idx < 3 * B.pl; idx += NT) A[idx] = make_double2(0., 0.);
   stage_plane(zb - 1, 0);
@@ -125,6 +133,18 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
   __syncthreads();
 
   const int cell = (ty + 1) * B.ex + (tx + 1);  // this thread's cell in an extended plane
+  // byte deltas to the periodic x-1 / x+1 and y-1 / y+1 neighbours (loop invariant); index 0: coordinate - 1 ... no:
+  // dxv[0] = offset of x+1 minus offset of x (used when c_x = -1, source = x+1), dxv[1] = offset of x-1 minus x
+  unsigned dxv[2], dyv[2], c_inpl;
+  {
+    const int xc = min(x, G.nx - 1), yc = min(y, G.ny - 1);
+    dxv[0] = (unsigned)((xc == G.nx - 1 ? -(G.nx - 1) : 1) * 8);
+    dxv[1] = (unsigned)((xc == 0 ? (G.nx - 1) : -1) * 8);
+    dyv[0] = (unsigned)((yc == G.ny - 1 ? -(G.ny - 1) : 1) * G.nx * 8);
+    dyv[1] = (unsigned)((yc == 0 ? (G.ny - 1) : -1) * G.nx * 8);
+    c_inpl = (unsigned)(yc * G.nx + xc) * 8u;
+  }
+  const unsigned pl8 = (unsigned)G.plane * 8u;
   for (int k = 0; k < vz; ++k) {
     const int zl = zb + k;
     // slot of plane zl + d : (k + 1 + d) % 3
@@ -156,14 +176,16 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
         // byte offsets of the 19 pull sources (x - c_i) inside a component; < 4 GiB is checked at creation
         unsigned off[Q];
         {
-          const unsigned xs[3] = {(unsigned)(x == 0 ? G.nx - 1 : x - 1), (unsigned)x, (unsigned)(x == G.nx - 1 ? 0 : x + 1)};
-          const unsigned yr[3] = {(unsigned)(y == 0 ? G.ny - 1 : y - 1) * (unsigned)G.nx, (unsigned)y * (unsigned)G.nx,
-                                  (unsigned)(y == G.ny - 1 ? 0 : y + 1) * (unsigned)G.nx};
-          const unsigned pl = (unsigned)G.plane;
-          const unsigned zp[3] = {(unsigned)zl * pl, (unsigned)(zl + 1) * pl, (unsigned)(zl + 2) * pl};
+          c = (unsigned)(zl + 1) * pl8 + c_inpl;
+          const unsigned dz[3] = {0u - pl8, 0u, pl8};
 #pragma unroll
-          for (int i = 0; i < Q; ++i) off[i] = (zp[1 - cz(i)] + yr[1 - cy(i)] + xs[1 - cx(i)]) * 8u;
-          c = off[0];
+          for (int i = 0; i < Q; ++i) {  // source = cell - c_i ; unsigned arithmetic wraps consistently
+            unsigned o = c;
+            if (cz(i) != 0) o += dz[1 - cz(i)];
+            if (cy(i) != 0) o += dyv[(1 + cy(i)) >> 1];
+            if (cx(i) != 0) o += dxv[(1 + cx(i)) >> 1];
+            off[i] = o;
+          }
         }
         if (PREFETCH && (tx & 15) == 0 && k + 1 < vz) {
           // next plane of this column into L2 (one request per 128 B line) while this plane computes
@@ -183,7 +205,7 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
           for (int i = 0; i < Q; ++i) f[i] = ld_off(X + (long long)i * G.comp, off[i]);
           moments(f, mf);
         }
-        nk = make_noise_key(P.seed, (unsigned long long)cell_global(G, x, y, zl), step);
+        nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
         collide_prepare<NOISE>(P, grho, gphi, nk, mf, mg, C);
         collide_species<NOISE, 0>(P, nk, C, mf);
       } else {
@@ -384,7 +406,7 @@ k_step_fused2(Geom G, BrickGrid B, DevParams P, long long step, const double* __
       NoiseKey nk;
       float n0[4] = {0.f, 0.f, 0.f, 0.f};
       if (NOISE) {
-        nk = make_noise_key(P.seed, (unsigned long long)cell_global(G, x, y, zl), step);
+        nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
         normals4(nk, 0, n0);
       }
       {

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) k_step_twopass(Geom G, DevParams P, long 
   }
   double grho[3], gphi[3];
   density_gradients(R, I, grho, gphi);
-  const NoiseKey nk = make_noise_key(P.seed, (unsigned long long)cell_global(G, x, y, zl), step);
+  const NoiseKey nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
   CollideCtx C;
   collide_prepare<NOISE>(P, grho, gphi, nk, mf, mg, C);
   const long long c = I.zpl[1] + I.yrow[1] + x;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) k_observe(Geom G, DevParams P, long long 
   const CellIdx I = cell_idx(G, x, y, zl);
   const long long oc = (long long)gridDim.z * G.plane;                       // component stride of the chunk
   const long long o = (long long)zc * G.plane + (long long)y * G.nx + x;    // cell offset in the chunk
-  const NoiseKey nk = make_noise_key(P.seed, (unsigned long long)cell_global(G, x, y, zl), step);
+  const NoiseKey nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
   if (MODE == OBS_NORMALS) {
     float n[36];
     cell_normals(nk, n);

@@ -28,6 +28,31 @@ __host__ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   return ctr;
 }
 
+// The same block function with the key schedule (key + r*W, identical for every thread) precomputed on the
+// host and passed as kernel constants: the round keys become constant-bank operands of the xor.
+struct PhiloxKeys {
+  uint32_t k0[BFLBM_PHILOX_ROUNDS], k1[BFLBM_PHILOX_ROUNDS];
+};
+inline PhiloxKeys philox_key_schedule(unsigned long long seed) {
+  PhiloxKeys K;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+  for (int r = 0; r < BFLBM_PHILOX_ROUNDS; ++r) {
+    K.k0[r] = a;
+    K.k1[r] = b;
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  return K;
+}
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, const PhiloxKeys& K) {
+#pragma unroll
+  for (int r = 0; r < BFLBM_PHILOX_ROUNDS; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * ctr.x, p1 = (uint64_t)0xCD9E8D57u * ctr.z;
+    ctr = make_uint4((uint32_t)(p1 >> 32) ^ ctr.y ^ K.k0[r], (uint32_t)p1, (uint32_t)(p0 >> 32) ^ ctr.w ^ K.k1[r], (uint32_t)p0);
+  }
+  return ctr;
+}
+
 // MUFU fast paths, flush-to-zero, no denormal/IEEE fix-up code around them
 __device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -52,12 +77,12 @@ __device__ __forceinline__ void box_muller(uint32_t u0, uint32_t u1, float& n0, 
 //   20..34  species g, modes a = 4..18 (blocks 5-8);  35 unused
 // draw_index() maps the reference's draw order (a = 4..18: f then g, interleaved) onto it.
 struct NoiseKey {
-  uint2 key;
+  const PhiloxKeys* K;  // points at the kernel parameter (constant bank)
   uint32_t cell_lo, cell_hi, step_lo, step_hi;
 };
-__device__ __forceinline__ NoiseKey make_noise_key(unsigned long long seed, unsigned long long cell, long long step) {
+__device__ __forceinline__ NoiseKey make_noise_key(const PhiloxKeys& K, unsigned long long cell, long long step) {
   NoiseKey k;
-  k.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  k.K = &K;
   k.cell_lo = (uint32_t)cell;
   k.cell_hi = (uint32_t)(cell >> 32);
   k.step_lo = (uint32_t)(unsigned long long)step;
@@ -70,7 +95,7 @@ __host__ __device__ constexpr int mode_index(int s, int a) { return 4 + 16 * s +
 __host__ __device__ constexpr int draw_index(int d) { return d < 3 ? d : mode_index((d - 3) & 1, 4 + ((d - 3) >> 1)); }
 
 __device__ __forceinline__ void normals4(const NoiseKey& k, int block, float (&n)[4]) {
-  const uint4 r = philox4x32(make_uint4(k.cell_lo, k.cell_hi, k.step_lo, k.step_hi | ((uint32_t)block << 24)), k.key);
+  const uint4 r = philox4x32(make_uint4(k.cell_lo, k.cell_hi, k.step_lo, k.step_hi | ((uint32_t)block << 24)), *k.K);
   box_muller(r.x, r.y, n[0], n[1]);
   box_muller(r.z, r.w, n[2], n[3]);
 }

@@ -21,7 +21,7 @@ struct DevParams {
   double acc_coef;        // -cs2 * alpha0                     LBM_binary.H:254-255
   double amp_j;           // A kBT,      A = 2(l - l^2/2), l = 1/(tau_f + 1/2)   LBM_binary.H:79-82,117
   double amp_s;           // A kBT / cs2                                          LBM_binary.H:125-126
-  unsigned long long seed;
+  PhiloxKeys keys;        // Philox round keys of the seed (LBM_binary.H:17)
 };
 
 struct CellHydro {

@@ -1,0 +1,232 @@
+"""Slab decomposition of the periodic box over the GPUs of one node: one process per GPU, torch.distributed
+for the plumbing (NCCL over NVLink for the ghost messages, gloo in the CPU tests).
+
+The reference's only parallelism is AMReX's box decomposition + FillBoundary (main_run_job.cpp:140-145,
+LBM_binary.H:130-131, 312, 353, 553-555: seven ghost fills of 19..22 components x 2 layers per step).
+Here the box is cut into P slabs along z (the slowest array axis, so ghost planes are contiguous) and ONE message
+of 14 doubles per face cell goes to each z-neighbour per step (include/bflbm.h, "slab halo exchange"):
+5+5 populations that stream across the face and the two (rho, phi) partial-sum planes.  There is no other
+collective on the data path; the noise is keyed by GLOBAL cell index, so results do not depend on P.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from .lattice import Lattice, Params, _check, NVEL
+
+
+def slab_bounds(nz_global: int, world: int, rank: int) -> tuple[int, int]:
+    """(z0, nz_local) of `rank`: contiguous, sizes differ by at most one plane (remainder to the low ranks)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, rem = divmod(nz_global, world)
+    if base < 2:
+        raise ValueError(f"nz={nz_global} is too small for {world} slabs (need >= 2 planes per slab)")
+    nzl = base + (1 if rank < rem else 0)
+    z0 = rank * base + min(rank, rem)
+    return z0, nzl
+
+
+def neighbours(world: int, rank: int) -> tuple[int, int]:
+    """(rank below, rank above) on the periodic ring; side 0 = towards lower z."""
+    return (rank - 1) % world, (rank + 1) % world
+
+
+def exchange_ring(send_lo, send_hi, recv_lo, recv_hi, rank: int, world: int, group=None):
+    """Moves send_lo -> lower neighbour's recv_hi and send_hi -> upper neighbour's recv_lo (periodic ring).
+    Tensors may live on the GPU (nccl) or the CPU (gloo).  One batched group of two sends and two receives,
+    which NCCL runs as a single fused kernel over NVLink."""
+    import torch.distributed as dist
+    if world == 1:
+        recv_hi.copy_(send_lo)
+        recv_lo.copy_(send_hi)
+        return
+    lo, hi = neighbours(world, rank)
+    ops = [dist.P2POp(dist.isend, send_lo, lo, group=group), dist.P2POp(dist.isend, send_hi, hi, group=group),
+           dist.P2POp(dist.irecv, recv_lo, lo, group=group), dist.P2POp(dist.irecv, recv_hi, hi, group=group)]
+    if world == 2:
+        # both neighbours are the same peer: order the two messages explicitly (send order = receive order)
+        ops = [dist.P2POp(dist.isend, send_lo, lo, group=group), dist.P2POp(dist.irecv, recv_hi, hi, group=group),
+               dist.P2POp(dist.isend, send_hi, hi, group=group), dist.P2POp(dist.irecv, recv_lo, lo, group=group)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+def _device_tensor(ptr: int, n: int, device):
+    """float64 torch view of `n` doubles of device memory owned by the C library."""
+    import torch
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 3, "strides": None}
+    return torch.as_tensor(h, device=device)
+
+
+class EmulatedSlabs:
+    """P slabs of one box held by ONE process on ONE GPU, stepped in lock-step with device-to-device copies in
+    place of the NCCL messages.  Exercises exactly the library path a multi-GPU run takes (bflbm_create_slab,
+    step_begin / step_end, halo buffers); used by the single-GPU tests of the slab logic."""
+
+    def __init__(self, nx, ny, nz, nslabs, params: Params | None = None, device: int = 0, brick_lz: int = 0):
+        import torch
+        self.world, self.nz_global = nslabs, nz
+        self.device = torch.device("cuda", device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.bounds = [slab_bounds(nz, nslabs, r) for r in range(nslabs)]
+        self.lats = [Lattice(nx, ny, nz, params=params, device=device, slab=b) for b in self.bounds]
+        for lat in self.lats:
+            lat.set_stream(self.stream.cuda_stream)
+            if brick_lz:
+                lat.set_tiling(brick_lz)
+        n = int(self.lats[0].lib.bflbm_halo_doubles(self.lats[0].h))
+        lib = self.lats[0].lib
+        self.send = [[_device_tensor(lib.bflbm_halo_send_buffer(l.h, s), n, self.device) for s in (0, 1)] for l in self.lats]
+        self.recv = [[_device_tensor(lib.bflbm_halo_recv_buffer(l.h, s), n, self.device) for s in (0, 1)] for l in self.lats]
+
+    def close(self):
+        for lat in self.lats:
+            lat.close()
+
+    def _exchange(self):
+        import torch
+        with torch.cuda.stream(self.stream):
+            for r in range(self.world):
+                lo, hi = neighbours(self.world, r)
+                self.recv[lo][1].copy_(self.send[r][0])  # my message towards lower z arrives from above at the lower neighbour
+                self.recv[hi][0].copy_(self.send[r][1])
+
+    def _all(self, name, *a):
+        for lat in self.lats:
+            getattr(lat, name)(*a)
+
+    def init_mixture(self):
+        self._all("init_mixture")
+
+    def init_stripe(self, frac=0.5):
+        self._all("init_stripe", frac)
+
+    def init_droplet(self, radius=0.2):
+        self._all("init_droplet", radius)
+
+    def init_from_global_populations(self, f, g):
+        for lat, (z0, nzl) in zip(self.lats, self.bounds):
+            idx = [(z % self.nz_global) for z in range(z0 - 1, z0 + nzl + 1)]
+            lat.init_from_populations_slab(np.ascontiguousarray(f[:, idx]), np.ascontiguousarray(g[:, idx]))
+        for lat in self.lats:
+            _check(lat.lib.bflbm_halo_refresh_begin(lat.h))
+        self._exchange()
+        for lat in self.lats:
+            _check(lat.lib.bflbm_halo_refresh_end(lat.h))
+
+    def step(self, n=1):
+        for _ in range(int(n)):
+            for lat in self.lats:
+                _check(lat.lib.bflbm_step_begin(lat.h))
+            self._exchange()
+            for lat in self.lats:
+                _check(lat.lib.bflbm_step_end(lat.h))
+
+    def gather(self, name):
+        """Concatenates a getter's result over the slabs along z (tuple results element-wise)."""
+        parts = [getattr(lat, name)() for lat in self.lats]
+        if isinstance(parts[0], tuple):
+            return tuple(np.concatenate([p[i] for p in parts], axis=1) for i in range(len(parts[0])))
+        axis = 0 if name == "normals" else 1
+        return np.concatenate(parts, axis=axis)
+
+
+class SlabLattice:
+    """One rank's slab of a periodic nx*ny*nz box.  Mirrors Lattice (init_*, step, getters on the local slab)."""
+
+    def __init__(self, nx, ny, nz, params: Params | None = None, device: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.group = group
+        self.nz_global = nz
+        self.z0, self.nzl = slab_bounds(nz, self.world, self.rank)
+        self.lat = Lattice(nx, ny, nz, params=params, device=device, slab=(self.z0, self.nzl))
+        self.device = torch.device("cuda", device)
+        # one stream for the library's kernels AND torch's collectives, so that pack -> send/recv -> unpack are ordered
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.lat.set_stream(self.stream.cuda_stream)
+        n = int(self.lat.lib.bflbm_halo_doubles(self.lat.h))
+        lib, h = self.lat.lib, self.lat.h
+        self.send = [_device_tensor(lib.bflbm_halo_send_buffer(h, s), n, self.device) for s in (0, 1)]
+        self.recv = [_device_tensor(lib.bflbm_halo_recv_buffer(h, s), n, self.device) for s in (0, 1)]
+        self.halo_bytes_per_step = 2 * n * 8
+
+    # -- delegation --------------------------------------------------------------------------------
+    def __getattr__(self, name):
+        return getattr(self.lat, name)
+
+    def _exchange(self):
+        import torch
+        with torch.cuda.stream(self.stream):
+            exchange_ring(self.send[0], self.send[1], self.recv[0], self.recv[1], self.rank, self.world, self.group)
+
+    def init_mixture(self):
+        self.lat.init_mixture()
+
+    def init_stripe(self, frac=0.5):
+        self.lat.init_stripe(frac)
+
+    def init_droplet(self, radius=0.2):
+        self.lat.init_droplet(radius)
+
+    def init_from_populations_slab(self, f_ghosted, g_ghosted):
+        self.lat.init_from_populations_slab(f_ghosted, g_ghosted)
+        _check(self.lat.lib.bflbm_halo_refresh_begin(self.lat.h))
+        self._exchange()
+        _check(self.lat.lib.bflbm_halo_refresh_end(self.lat.h))
+
+    def init_from_global_populations(self, f, g):
+        """Convenience for tests: every rank passes the WHOLE box (19, nz, ny, nx) and keeps its slab + ghost planes."""
+        idx = [(z % self.nz_global) for z in range(self.z0 - 1, self.z0 + self.nzl + 1)]
+        self.init_from_populations_slab(np.ascontiguousarray(f[:, idx]), np.ascontiguousarray(g[:, idx]))
+
+    def step(self, n=1):
+        lib, h = self.lat.lib, self.lat.h
+        for _ in range(int(n)):
+            _check(lib.bflbm_step_begin(h))
+            self._exchange()
+            _check(lib.bflbm_step_end(h))
+
+    def run_e2e(self, nsteps, out_pinned, pinned):
+        """bench.py helper: restart upload + nsteps + hydrovsbar download on this slab, host buffers."""
+        import time
+        import torch
+        import torch.distributed as dist
+        lat = self.lat
+        f, g = lat.populations()  # untimed: makes the host checkpoint of this slab
+        # ghost planes of the host checkpoint come from the ring neighbours (host-side exchange through the GPUs' path
+        # would hide the cost, so it is done here once, untimed, like reading a checkpoint file that already has them)
+        fg = np.empty((2, NVEL, self.nzl + 2, lat.ny, lat.nx))
+        fg[0, :, 1:-1], fg[1, :, 1:-1] = f, g
+        lo_send = torch.from_numpy(np.ascontiguousarray(np.stack([f[:, 0], g[:, 0]]))).to(self.device)
+        hi_send = torch.from_numpy(np.ascontiguousarray(np.stack([f[:, -1], g[:, -1]]))).to(self.device)
+        lo_recv, hi_recv = torch.empty_like(lo_send), torch.empty_like(hi_send)
+        exchange_ring(lo_send, hi_send, lo_recv, hi_recv, self.rank, self.world, self.group)
+        fg[:, :, 0] = lo_recv.cpu().numpy()
+        fg[:, :, -1] = hi_recv.cpu().numpy()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        self.init_from_populations_slab(fg[0], fg[1])
+        self.step(nsteps)
+        _check(lat.lib.bflbm_get_hydrovars_bar(lat.h, out_pinned.numpy().ctypes.data))
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=self.device, dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        cells_local = self.nzl * lat.ny * lat.nx
+        cells = lat.nx * lat.ny * self.nz_global
+        return {"value": cells * nsteps / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 2 * 19 * 8 * (cells_local + 2 * lat.ny * lat.nx) / nsteps,
+                "d2h_bytes_per_step": 9 * 8 * cells_local / nsteps, "steps_per_interval": nsteps, "seconds": dt, "pinned_host": pinned,
+                "what": "per rank: bflbm_init_from_populations_slab(host f,g) + halo refresh + nsteps x (step_begin, NCCL ring exchange, "
+                        "step_end) + bflbm_get_hydrovars_bar(host); wall clock, max over ranks"}

@@ -284,3 +284,52 @@ def test_center_of_mass_and_mass(bflbm, oracle_mod):
         c, sums = lat.center_of_mass()
         assert np.allclose(c, com, rtol=1e-12)
         assert abs(sums[0] - rho.sum()) < 1e-12 * rho.sum()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# slab decomposition (the multi-GPU path), emulated on one GPU: P slabs, device-to-device copies instead of NCCL
+@pytest.mark.parametrize("nslabs", [2, 3, 4])
+@pytest.mark.parametrize("kbt", [0.0, 1e-5])
+def test_slabs_bitwise_equal_to_whole_box(bflbm, nslabs, kbt):
+    """results must not depend on the number of slabs.  Same brick height => bit-identical."""
+    from bflbm_b200.distributed import EmulatedSlabs
+    shape = (20, 12, 24)
+    prm = bflbm.Params(kBT=kbt, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, tau_f=0.7, tau_g=0.55, seed=99)
+    with bflbm.Lattice(*shape, params=prm) as whole:
+        whole.set_tiling(2)
+        whole.init_droplet(0.3)
+        S = EmulatedSlabs(*shape, nslabs, params=prm, brick_lz=2)
+        try:
+            S.init_droplet(0.3)
+            for _ in range(3):
+                whole.step(2)
+                S.step(2)
+                fw, gw = whole.populations()
+                fs, gs = S.gather("populations")
+                assert np.array_equal(fw, fs) and np.array_equal(gw, gs)
+                assert np.array_equal(whole.hydrovars(), S.gather("hydrovars"))
+            if kbt > 0:
+                assert np.array_equal(whole.normals(), S.gather("normals")), "noise is keyed by the GLOBAL cell index"
+        finally:
+            S.close()
+
+
+def test_slabs_restart_from_populations(bflbm, oracle_mod):
+    """LBM_init (restart) on slabs: ghosted upload + halo refresh, then parity with the oracle."""
+    from bflbm_b200.distributed import EmulatedSlabs
+    shape = (16, 8, 18)
+    prm = dict(kBT=0.0, tau_f=0.5, tau_g=0.5, alpha0=1.5, alpha1=0.0, kappa=0.1, rho_lo=0.1, rho_hi=3.0)
+    O = oracle_mod.PortOracle(*shape)
+    O.set_params(**prm)
+    O.init_stripe(0.5)
+    O.step(2)
+    f, g = O.populations()
+    S = EmulatedSlabs(*shape, 3, params=bflbm.Params(**prm))
+    try:
+        S.init_from_global_populations(f, g)
+        assert_hydro_close(S.gather("hydrovars"), O.hydrovars(), TOL, "slab restart")
+        S.step(3)
+        O.step(3)
+        assert_hydro_close(S.gather("hydrovars"), O.hydrovars(), 10 * TOL, "slab restart + 3 steps")
+    finally:
+        S.close()
