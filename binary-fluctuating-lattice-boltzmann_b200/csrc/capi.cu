@@ -45,7 +45,7 @@ struct bflbm_lattice {
   int device = 0;
   bool whole_box = true;
   bool initialized = false;
-  int algo = 0;  // 0 fused (two threads per cell), 1 two-pass, 2 fused (one thread per cell)
+  int algo = 0;  // 0 fused (one thread per cell), 1 two-pass, 2 fused, species-split (two threads per cell)
   int lz_request = 0;
   int cta_threads = 256;  // threads per CTA of the fused kernel (BFLBM_CTA_THREADS=128|256)
   bool prefetch = false;  // L2 prefetch of the next plane in the fused kernel (BFLBM_PREFETCH=1)
@@ -97,14 +97,14 @@ cudaError_t set_fused_smem_nt(int bytes) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused<false, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   return e;
 }
+// dynamic shared memory of the fused kernels for brick shape B (set for every variant: the choice is made at launch)
 cudaError_t set_fused_smem(const BrickGrid& B) {
-  if (B.tx * B.ty == 128 && B.tx <= 16) {  // species-split kernel (its smem fits the default limit, set anyway)
-    cudaError_t e = cudaFuncSetAttribute(k_step_fused2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused2_smem_bytes(B));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused2_smem_bytes(B));
-    return e;
-  }
+  cudaError_t e = cudaFuncSetAttribute(k_step_fused2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused2_smem_bytes(B));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused2_smem_bytes(B));
   const int bytes = (int)fused_smem_bytes(B);
-  return B.tx * B.ty == 128 ? set_fused_smem_nt<128>(bytes) : set_fused_smem_nt<256>(bytes);
+  if (e == cudaSuccess) e = set_fused_smem_nt<128>(bytes);
+  if (e == cudaSuccess) e = set_fused_smem_nt<256>(bytes);
+  return e;
 }
 
 inline void mark(bflbm_lattice* h, int i) {
@@ -309,7 +309,7 @@ int fold_local(bflbm_lattice* h) {
 template <bool NOISE>
 int launch_fused(bflbm_lattice* h) {
   const BrickGrid& B = h->B;
-  if (h->algo == 0) {
+  if (h->algo == 2) {
     dim3 grid(B.bx, B.by, B.bz);
     k_step_fused2<NOISE><<<grid, 256, fused2_smem_bytes(B), h->stream>>>(h->G, B, h->dp, h->step, h->X[h->cur], h->X[1 - h->cur], h->R, h->E);
     ++h->launches;
@@ -402,7 +402,7 @@ int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, 
     const char* nt = getenv("BFLBM_CTA_THREADS");
     h->cta_threads = (nt && atoi(nt) == 128) ? 128 : 256;
   }
-  h->B = make_brick_grid(G, 0, 128, 16);  // default algorithm: species-split fused kernel, 16x8 cells per CTA plane
+  h->B = make_brick_grid(G, 0, h->cta_threads, 32);
   TRY(dev_alloc(h, &h->E, brick_doubles2(h->B)));
   h->halo_doubles = (size_t)14 * G.plane;
   for (int s = 0; s < 2; ++s) {
@@ -560,7 +560,7 @@ int bflbm_set_stream(bflbm_lattice* h, void* s) {
 }
 int bflbm_set_algorithm(bflbm_lattice* h, int algo) {
   CHECK_H(h);
-  if (algo < 0 || algo > 2) return fail(BFLBM_ERR_ARG, "algorithm must be 0 (fused), 1 (two-pass) or 2 (fused, one thread per cell)");
+  if (algo < 0 || algo > 2) return fail(BFLBM_ERR_ARG, "algorithm must be 0 (fused), 1 (two-pass) or 2 (fused, two threads per cell)");
   if (algo == 1 && !h->whole_box) return fail(BFLBM_ERR_ARG, "the two-pass algorithm supports whole-box lattices only");
   h->algo = algo;
   return bflbm_set_tiling(h, h->lz_request);  // the brick shape depends on the kernel
@@ -573,7 +573,7 @@ int bflbm_set_tiling(bflbm_lattice* h, int brick_lz) {
   int rc = set_device(h);
   if (rc) return rc;
   CU(cudaStreamSynchronize(h->stream));
-  const BrickGrid nb = h->algo == 0 ? make_brick_grid(h->G, brick_lz, 128, 16) : make_brick_grid(h->G, brick_lz, h->cta_threads, 32);
+  const BrickGrid nb = h->algo == 2 ? make_brick_grid(h->G, brick_lz, 128, 16) : make_brick_grid(h->G, brick_lz, h->cta_threads, 32);
   if (brick_doubles2(nb) != brick_doubles2(h->B)) {
     CU(cudaFree(h->E));
     h->bytes -= brick_doubles2(h->B) * sizeof(double2);
@@ -668,6 +668,8 @@ int bflbm_step_end(bflbm_lattice* h) {
   if (rc) return rc;
   double* const self[2] = {h->send[1], h->send[0]};
   if ((rc = unpack_halo(h, h->whole_box ? self : h->recv))) return rc;
+  mark(h, 4);
+  profile_collect(h);  // interval 3 (pack end -> unpack end) contains the caller's exchange
   ++h->step;
   return 0;
 }

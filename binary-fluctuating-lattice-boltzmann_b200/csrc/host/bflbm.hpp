@@ -1,0 +1,106 @@
+// C++ host-side mirror of the reference's solver interface over the C ABI (include/bflbm.h).
+//
+// The reference's driver calls header-inline functions on caller-owned MultiFabs:
+//   LBM_init_mixture / LBM_init_stripe / LBM_init_droplet / LBM_init / LBM_timestep / LBM_hydrovars /
+//   LBM_hydrovars_density / thermal_noise / update_com      (LBM_binary.H:73-742, LBM_hydrovs.H:26-60)
+// plus globals kBT, tau_f, tau_g, alpha0, alpha1, kappa, seed (LBM_d3q19.H:10, LBM_binary.H:17-30).
+// bflbm::Lattice bundles what those MultiFabs hold (device resident) and the free functions below keep the
+// reference's names and argument meaning, so a driver written against LBM_binary.H ports line by line.
+// Errors: the reference returns void and exit(0)s on NaN (Debug.H:137-149); here every failure throws bflbm::Error.
+#pragma once
+#include <array>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../../include/bflbm.h"
+
+namespace bflbm {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc) {
+  if (rc != 0) throw Error(rc, std::string("bflbm: ") + bflbm_last_error());
+}
+
+// the reference's global parameters, with its shipped defaults
+inline bflbm_params default_params() {
+  bflbm_params p;
+  check(bflbm_params_default(&p));
+  return p;
+}
+
+class Lattice {
+ public:
+  Lattice(const bflbm_params& p, int nx, int ny, int nz, int device = 0) : nx_(nx), ny_(ny), nz_(nz) {
+    check(bflbm_create(&p, nx, ny, nz, device, &h_));
+  }
+  ~Lattice() { bflbm_destroy(h_); }
+  Lattice(const Lattice&) = delete;
+  Lattice& operator=(const Lattice&) = delete;
+
+  int nx() const { return nx_; }
+  int ny() const { return ny_; }
+  int nz() const { return nz_; }
+  size_t cells() const { return (size_t)nx_ * ny_ * nz_; }
+  bflbm_lattice* handle() const { return h_; }
+  long long step_count() const { return bflbm_step_count(h_); }
+  void set_params(const bflbm_params& p) { check(bflbm_set_params(h_, &p)); }
+  bflbm_params params() const { bflbm_params p; check(bflbm_get_params(h_, &p)); return p; }
+  void sync() { check(bflbm_sync(h_)); }
+
+  // FAB-order host arrays (x fastest ... component slowest), valid region
+  std::vector<double> hydrovars() { std::vector<double> v(BFLBM_NHYDRO * cells()); check(bflbm_get_hydrovars(h_, v.data())); return v; }
+  std::vector<double> hydrovars_bar() { std::vector<double> v(BFLBM_NHYDRO_BAR * cells()); check(bflbm_get_hydrovars_bar(h_, v.data())); return v; }
+  std::pair<std::vector<double>, std::vector<double>> populations() {
+    std::vector<double> f(BFLBM_NVEL * cells()), g(BFLBM_NVEL * cells());
+    check(bflbm_get_populations(h_, f.data(), g.data()));
+    return {std::move(f), std::move(g)};
+  }
+  std::pair<std::vector<double>, std::vector<double>> noise() {
+    std::vector<double> f(BFLBM_NVEL * cells()), g(BFLBM_NVEL * cells());
+    check(bflbm_get_noise(h_, f.data(), g.data()));
+    return {std::move(f), std::move(g)};
+  }
+
+ private:
+  bflbm_lattice* h_ = nullptr;
+  int nx_, ny_, nz_;
+};
+
+// ---- the reference's entry points (same names; the MultiFab bundle is the Lattice) -------------------
+inline void LBM_init_mixture(Lattice& L) { check(bflbm_init_mixture(L.handle())); }                      // LBM_binary.H:598
+inline void LBM_init_stripe(double frac, Lattice& L) { check(bflbm_init_stripe(L.handle(), frac)); }     // LBM_binary.H:664
+inline void LBM_init_droplet(double r, Lattice& L) { check(bflbm_init_droplet(L.handle(), r)); }         // LBM_binary.H:699
+inline void LBM_init(Lattice& L, const std::vector<double>& f0, const std::vector<double>& g0) {        // LBM_binary.H:632
+  if (f0.size() != BFLBM_NVEL * L.cells() || g0.size() != f0.size()) throw Error(BFLBM_ERR_ARG, "LBM_init: population array size");
+  check(bflbm_init_from_populations(L.handle(), f0.data(), g0.data()));
+}
+inline void LBM_timestep(Lattice& L, int nsteps = 1) { check(bflbm_step(L.handle(), nsteps)); }           // LBM_binary.H:545
+inline std::vector<double> LBM_hydrovars(Lattice& L) { return L.hydrovars(); }                            // LBM_binary.H:298
+inline std::vector<double> LBM_hydrovars_density(Lattice& L) { return L.hydrovars_bar(); }                // LBM_binary.H:343
+inline std::pair<std::vector<double>, std::vector<double>> thermal_noise(Lattice& L) { return L.noise(); }  // LBM_binary.H:74
+inline std::array<double, 3> update_com(Lattice& L) {                                                     // LBM_hydrovs.H:27
+  std::array<double, 3> c;
+  check(bflbm_center_of_mass(L.handle(), c.data(), nullptr));
+  return c;
+}
+// MultiFabNANCheck (Debug.H:136-149): throws instead of exit(0)
+inline void MultiFabNANCheck(Lattice& L) {
+  long long n = 0;
+  check(bflbm_check_nan(L.handle(), &n));
+}
+
+// hydrovs component names, AMReX_FileIO.H:208-261
+inline std::vector<std::string> VariableNames(int n = BFLBM_NHYDRO) {
+  static const char* names[BFLBM_NHYDRO] = {"rho", "phi", "ufx", "ufy", "ufz", "p_bulk", "ugx", "ugy", "ugz", "afx", "afy",
+                                            "afz", "agx", "agy", "agz", "ubx", "uby", "ubz", "nfbarx", "ngbarx", "ufbarx", "ugbarx"};
+  std::vector<std::string> v;
+  for (int i = 0; i < n && i < BFLBM_NHYDRO; ++i) v.push_back(names[i]);
+  return v;
+}
+
+}  // namespace bflbm

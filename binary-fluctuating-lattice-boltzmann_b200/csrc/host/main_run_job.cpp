@@ -1,0 +1,178 @@
+// Host driver: the B200 counterpart of the reference's main_run_job.cpp.  Same job structure -- parameters,
+// init (default state or checkpoint restart), NaN check, time loop with print/plot cadence, checkpoint, run-time
+// print, equilibrium extraction at kBT = 0 -- but the parameters come from a real input file, the solver calls go
+// through the C ABI (include/bflbm.h) to the CUDA path, and the MultiFabs are device resident.
+//
+//   bflbm_run_job <Parameters file> [key=value ...]      (trailing key=value pairs override the file)
+//
+// File names follow main_run_job.cpp:150-202 (plot_file_dir, lbm_data_shshan_alpha0_.._xi_.._size.., f_checkpoint..).
+// Out of scope: FHDeX StructFact, droplet radius fit.
+#include <chrono>
+#include <cstdarg>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <sstream>
+
+#include "bflbm.hpp"
+#include "parameters.hpp"
+#include "plotfile.hpp"
+
+using namespace bflbm;
+
+static std::string fmt(const char* f, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof buf, f, ap);
+  va_end(ap);
+  return buf;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    std::fprintf(stderr, "usage: %s <Parameters file> [key=value ...]\n", argv[0]);
+    return 2;
+  }
+  try {
+    std::stringstream text;
+    {
+      std::ifstream in(argv[1]);
+      if (!in) throw std::runtime_error(std::string("cannot open ") + argv[1]);
+      text << in.rdbuf() << '\n';
+      for (int i = 2; i < argc; ++i) text << argv[i] << '\n';
+    }
+    const RunParameters R = parse_parameters(text);
+    const bool noiseSwitch = R.kBT != 0.;  // main_run_job.cpp:63
+    const auto t_start = std::chrono::steady_clock::now();
+
+    bflbm_params p = default_params();
+    p.kBT = R.kBT; p.tau_f = R.tau_f; p.tau_g = R.tau_g; p.alpha0 = R.alpha0; p.alpha1 = R.alpha1; p.kappa = R.kappa;
+    p.rho_lo = R.rho_lo; p.rho_hi = R.rho_hi; p.seed = R.seed; p.step0 = R.step_continue;
+    const int nx = R.nx, ny = R.ny, nz = R.nz;
+    std::printf("%s\n", bflbm_version());
+    std::printf("system = %s, box = %d x %d x %d, alpha0 = %g, kBT = %g, tau_f = %g, tau_g = %g\n", R.system.c_str(), nx, ny, nz, R.alpha0, R.kBT, R.tau_f, R.tau_g);
+    if (R.plot_SF_window == 0) std::printf("plot_SF_window = 0 and No stuct factor will be calculated\n");
+
+    // ---- file names, main_run_job.cpp:150-202 --------------------------------------------------------
+    std::string plot_file_dir;
+    if (R.system == "flat_interface") plot_file_dir = fmt("data_interface_alpha0_%.2f", R.alpha0);
+    else if (R.system == "droplet") plot_file_dir = fmt("data_droplet_density_%.2f_alpha0_%.2f_r%.3f_size%d-%d-%d", R.rho_hi, R.alpha0, R.radius, nx, ny, nz);
+    else plot_file_dir = std::string("data_mixture") + (R.plot_fields == "hydrovars" ? "_hydrovars" : "_lb_hydrovars");
+    const std::string size_tag = fmt("_size%d-%d-%d", nx, ny, nz);
+    const std::string base = R.root_path + "/" + plot_file_dir;
+    const std::string plot_file_root = base + fmt("/lbm_data_shshan_alpha0_%.2f_xi_%.1e", R.alpha0, R.kBT) + size_tag + (noiseSwitch ? "_continue/plt" : "/plt");
+    auto chk_name = [&](const char* which, int step, double temp) {
+      return concatenate(base + "/" + which + "_checkpoint", step, R.Ndigits) + fmt("_alpha0_%.2f_xi_%.1e", R.alpha0, temp) + size_tag;
+    };
+    auto eq_name = [&](const char* which) { return base + "/equilibrium_" + which + fmt("_alpha0_%.2f", R.alpha0) + size_tag; };
+
+    Lattice L(p, nx, ny, nz, R.device);
+
+    // ---- initialise, main_run_job.cpp:245-292 ------------------------------------------------------------
+    if (R.if_continue_from_last_frame) {
+      const double chk_temp = R.continueFromNonFluct ? 0. : R.kBT;
+      std::printf("Loading in last frame checkpoint files....\n");
+      const PlotfileData F = read_plotfile(chk_name("f", R.step_continue, chk_temp));
+      const PlotfileData G = read_plotfile(chk_name("g", R.step_continue, chk_temp));
+      if (F.nx != nx || F.ny != ny || F.nz != nz || F.ncomp != BFLBM_NVEL) throw std::runtime_error("checkpoint does not match the box");
+      LBM_init(L, F.data, G.data);
+    } else if (R.system == "mixture") {
+      std::printf("Init mixture system ...\n");
+      LBM_init_mixture(L);
+    } else if (R.system == "flat_interface") {
+      std::printf("Init flate interface system ...\n");
+      LBM_init_stripe(R.init_frac, L);
+    } else {
+      std::printf("Init droplet system ...\n");
+      LBM_init_droplet(R.radius, L);
+    }
+    std::printf("check initial hydrodynamic quantities validity ...\n");
+    MultiFabNANCheck(L);  // main_run_job.cpp:294-297 (throws instead of exit(0))
+
+    const bool plot_real = R.plot_fields == "hydrovars";
+    auto write_output = [&](int step) {  // WriteOutput, main_run_job.cpp:35-55
+      const std::string dir = concatenate(plot_file_root, step, R.Ndigits);
+      if (plot_real) write_plotfile(dir, L.hydrovars(), BFLBM_NHYDRO, nx, ny, nz, VariableNames(BFLBM_NHYDRO), step, step);
+      else           write_plotfile(dir, L.hydrovars_bar(), BFLBM_NHYDRO_BAR, nx, ny, nz, VariableNames(BFLBM_NHYDRO_BAR), step, step);
+    };
+    if (R.plot_int > 0 && R.step_continue == 0) write_output(0);
+    std::printf("LB initialized with alpha0 = %g and T = %g\n", R.alpha0, R.kBT);
+
+    // ---- time loop, main_run_job.cpp:329-387 ------------------------------------------------------------------
+    const auto t_loop = std::chrono::steady_clock::now();
+    const int last = R.step_continue + R.nsteps;
+    int step = R.step_continue;
+    while (step < last) {
+      // run up to the next step at which the host has to look at the state
+      int next = last;
+      auto upto = [&](int interval) {
+        if (interval > 0) next = std::min(next, (step / interval + 1) * interval);
+      };
+      upto(R.print_int);
+      upto(R.plot_int);
+      if (noiseSwitch) upto(R.out_noise_step);
+      LBM_timestep(L, next - step);
+      step = next;
+      if (R.print_int > 0 && step % R.print_int == 0) std::printf("LB step %d info:\n", step);
+      if (noiseSwitch && R.out_noise_step > 0 && step % R.out_noise_step == 0) {  // WriteOutNoise, Debug.H:380-409
+        auto nz2 = L.noise();
+        std::vector<std::string> fa, ga;
+        for (int a = 0; a < BFLBM_NVEL; ++a) { fa.push_back("fa" + std::to_string(a)); ga.push_back("ga" + std::to_string(a)); }
+        write_plotfile(concatenate(plot_file_root + "_fnoise", step, R.Ndigits), nz2.first, BFLBM_NVEL, nx, ny, nz, fa, step, step);
+        write_plotfile(concatenate(plot_file_root + "_gnoise", step, R.Ndigits), nz2.second, BFLBM_NVEL, nx, ny, nz, ga, step, step);
+      }
+      if (R.plot_int > 0 && step % R.plot_int == 0) {
+        std::printf("\t**************************************\t\n\tLB step %d & Output\n\t**************************************\t\n", step);
+        if (R.system == "droplet") {
+          const auto c = update_com(L);
+          std::printf("Center of Mass: (%g,%g,%g)\n", c[0], c[1], c[2]);
+        }
+        if (step >= R.out_step && step != last) write_output(step);
+      }
+      if (step == last) write_output(step);
+    }
+    L.sync();
+    const double loop_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
+
+    // ---- checkpoint, main_run_job.cpp:398-409 ---------------------------------------------------------------------
+    {
+      auto fg = L.populations();
+      write_plotfile(chk_name("f", last, R.kBT), fg.first, BFLBM_NVEL, nx, ny, nz, {"rho_chk"}, 0, 0);
+      write_plotfile(chk_name("g", last, R.kBT), fg.second, BFLBM_NVEL, nx, ny, nz, {"phi_chk"}, 0, 0);
+    }
+    MultiFabNANCheck(L);
+    const double run_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    std::printf("Run time = %g\n", run_s);  // main_run_job.cpp:418-420
+    std::printf("time loop: %d steps in %g s = %.1f MLUPS (incl. output)\n", R.nsteps, loop_s, (double)L.cells() * R.nsteps / loop_s / 1e6);
+
+    // ---- equilibrium state = ensemble mean of the saved frames, main_run_job.cpp:422-439 / Debug.H:275-358 -------
+    if (!noiseSwitch && R.plot_int > 0) {
+      const int step1 = last - R.t_window, step2 = last;
+      const int comp_of[3] = {0, 1, 5};  // rho, phi, rho+phi
+      const char* nm[3] = {"rho", "phi", "rhot"};
+      std::vector<std::vector<double>> mean(3, std::vector<double>(L.cells(), 0.));
+      int frames = 0;
+      for (int s = std::max(step1, R.out_step); s <= step2; s += R.plot_int) {
+        if (s % R.plot_int != 0) continue;
+        PlotfileData F;
+        try { F = read_plotfile(concatenate(plot_file_root, s, R.Ndigits)); } catch (const std::exception&) { continue; }
+        for (int k = 0; k < 3; ++k)
+          for (size_t i = 0; i < L.cells(); ++i) mean[k][i] += F.data[(size_t)comp_of[k] * L.cells() + i];
+        ++frames;
+      }
+      if (frames > 0) {
+        for (int k = 0; k < 3; ++k) {
+          for (auto& v : mean[k]) v /= frames;
+          write_plotfile(eq_name(nm[k]), mean[k], 1, nx, ny, nz, {std::string(nm[k]) + "_eq"}, 0, 0);
+        }
+        std::printf("equilibrium state: mean of %d frames in steps [%d, %d]\n", frames, step1, step2);
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "bflbm_run_job: %s\n", e.what());
+    return 1;
+  }
+}

@@ -79,8 +79,8 @@ int bflbm_get_params(const bflbm_lattice* h, bflbm_params* p);
 
 /* Use the caller's CUDA stream (a cudaStream_t) for all subsequent work; NULL = the library's own. */
 int bflbm_set_stream(bflbm_lattice* h, void* cuda_stream);
-/* 0 = one-pass fused step, two threads per cell (default); 1 = two-pass step (density kernel + collide/stream
- * kernel, whole-box lattices only); 2 = one-pass fused step, one thread per cell. */
+/* 0 = one-pass fused step, one thread per cell (default); 1 = two-pass step (density kernel + collide/stream
+ * kernel, whole-box lattices only); 2 = one-pass fused step, species-split (two threads per cell). */
 int bflbm_set_algorithm(bflbm_lattice* h, int algo);
 /* Height (planes) of the CTA bricks of the fused step; 0 = automatic.  Results are bit-identical for any
  * number of slabs as long as every slab uses the same brick height and it divides nz_local. */

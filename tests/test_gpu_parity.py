@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-12
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-ALGOS = ["fused", "fused1", "twopass"]
+ALGOS = ["fused", "fused2", "twopass"]
 
 
 def params_of(d):
