@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--nx", type=int, default=512)
     ap.add_argument("--ny", type=int, default=512)
     ap.add_argument("--nz", type=int, default=512, help="planes PER GPU (weak scaling)")
-    ap.add_argument("--algo", default="fused", choices=["fused", "fused2", "twopass"])
+    ap.add_argument("--algo", default="fused", choices=["fused", "twopass"])
     ap.add_argument("--kbt", type=float, default=PARAMS["kBT"])
     ap.add_argument("--brick-lz", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
@@ -249,7 +249,7 @@ def run_b200(a):
     if nprof > 0 and per_kernel[0] > 0:
         achieved = BYTES_PER_CELL * cells_local / (per_kernel[0] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "peak_source": peak_src, "kernel": {"fused": "k_step_fused", "fused2": "k_step_fused2", "twopass": "k_step_twopass"}[a.algo],
+                    "peak_source": peak_src, "kernel": {"fused": "k_step_fused", "twopass": "k_step_twopass"}[a.algo],
                     "kernel_ms": per_kernel[0], "other_kernels_ms": {"fold_or_wrap": per_kernel[1], "pack_or_density": per_kernel[2],
                                                                      "unpack_or_wrap": per_kernel[3]},
                     "algorithmic_bytes_per_cell": BYTES_PER_CELL,

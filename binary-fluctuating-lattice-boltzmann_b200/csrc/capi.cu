@@ -45,10 +45,10 @@ struct bflbm_lattice {
   int device = 0;
   bool whole_box = true;
   bool initialized = false;
-  int algo = 0;  // 0 fused (one thread per cell), 1 two-pass, 2 fused, species-split (two threads per cell)
+  int algo = 0;  // 0 fused one-pass, 1 two-pass
   int lz_request = 0;
   int cta_threads = 256;  // threads per CTA of the fused kernel (BFLBM_CTA_THREADS=128|256)
-  bool prefetch = false;  // L2 prefetch of the next plane in the fused kernel (BFLBM_PREFETCH=1)
+  bool rate1_fast_path = true;  // use the rate == 1 specialisation when tau_f = tau_g = 1/2 (BFLBM_RATE1=0 disables it)
   long long step = 0;
   long long launches = 0;
   size_t bytes = 0;
@@ -62,7 +62,11 @@ struct bflbm_lattice {
 
   // fused algorithm
   BrickGrid B{};
-  double2* E = nullptr;
+  double2* E[2] = {nullptr, nullptr};  // extended boxes of the last two steps (ping-pong): E[ecur] is the newest
+  int ecur = 0;
+  bool e_valid = false;        // E[ecur] holds the densities of the current state (the step kernel may fold from it)
+  bool r_stale = false;        // R is current only on brick-face planes; k_fold<2>(E[ecur]) completes it on demand
+  bool fold_in_staging = true; // BFLBM_FOLD_IN_STAGING=0: separate full fold pass every step (first design)
 
   // halo messages (slab) : [side] ; layout see pack_halo()
   double* send[2] = {nullptr, nullptr};
@@ -89,21 +93,23 @@ namespace {
 
 int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-template <int NT>
-cudaError_t set_fused_smem_nt(int bytes) {
-  cudaError_t e = cudaFuncSetAttribute(k_step_fused<true, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused<true, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused<false, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused<false, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+// the eight variants of the step kernel for one CTA size; F = kernel functor applied to each instantiation
+template <int NT, class Fn>
+cudaError_t for_each_fused(Fn fn) {
+  cudaError_t e = cudaSuccess;
+#define BFLBM_EACH(N, R1, FU) if (e == cudaSuccess) e = fn((const void*)k_step_fused<N, R1, FU, NT>, R1)
+  BFLBM_EACH(false, false, false); BFLBM_EACH(false, false, true); BFLBM_EACH(false, true, false); BFLBM_EACH(false, true, true);
+  BFLBM_EACH(true, false, false);  BFLBM_EACH(true, false, true);  BFLBM_EACH(true, true, false);  BFLBM_EACH(true, true, true);
+#undef BFLBM_EACH
   return e;
 }
 // dynamic shared memory of the fused kernels for brick shape B (set for every variant: the choice is made at launch)
 cudaError_t set_fused_smem(const BrickGrid& B) {
-  cudaError_t e = cudaFuncSetAttribute(k_step_fused2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused2_smem_bytes(B));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused2_smem_bytes(B));
-  const int bytes = (int)fused_smem_bytes(B);
-  if (e == cudaSuccess) e = set_fused_smem_nt<128>(bytes);
-  if (e == cudaSuccess) e = set_fused_smem_nt<256>(bytes);
+  auto set = [&](const void* k, bool rate1) {
+    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes(B, rate1));
+  };
+  cudaError_t e = for_each_fused<128>(set);
+  if (e == cudaSuccess) e = for_each_fused<256>(set);
   return e;
 }
 
@@ -298,40 +304,58 @@ int unpack_halo(bflbm_lattice* h, double* const recv[2]) {
   return 0;
 }
 
-int fold_local(bflbm_lattice* h) {
+// mode 0: all planes; 1: brick-face planes + slab-face outputs; 2: the complement of 1
+int fold_local(bflbm_lattice* h, int mode) {
   const Geom& G = h->G;
-  k_fold<<<cell_grid(h, G.nzl + 2), h->block, 0, h->stream>>>(G, h->B, h->E, h->R);
+  const dim3 grid(h->B.bx, h->B.by, h->B.bz), block(h->B.tx, h->B.ty);
+  if (mode == 0)      k_fold<0><<<grid, block, 0, h->stream>>>(G, h->B, h->E[h->ecur], h->R);
+  else if (mode == 1) k_fold<1><<<grid, block, 0, h->stream>>>(G, h->B, h->E[h->ecur], h->R);
+  else                k_fold<2><<<grid, block, 0, h->stream>>>(G, h->B, h->E[h->ecur], h->R);
   ++h->launches;
   CU(cudaGetLastError());
   return 0;
 }
+// R complete on every plane (observers, diagnostics, kernels that stage every plane from R)
+int ensure_full_R(bflbm_lattice* h) {
+  if (!h->r_stale) return 0;
+  int rc = fold_local(h, 2);
+  if (rc) return rc;
+  h->r_stale = false;
+  return 0;
+}
 
-template <bool NOISE>
-int launch_fused(bflbm_lattice* h) {
+template <bool NOISE, bool R1, bool FU>
+int launch_fused_v(bflbm_lattice* h) {
   const BrickGrid& B = h->B;
-  if (h->algo == 2) {
-    dim3 grid(B.bx, B.by, B.bz);
-    k_step_fused2<NOISE><<<grid, 256, fused2_smem_bytes(B), h->stream>>>(h->G, B, h->dp, h->step, h->X[h->cur], h->X[1 - h->cur], h->R, h->E);
-    ++h->launches;
-    CU(cudaGetLastError());
-    return 0;
-  }
-  dim3 grid(B.bx, B.by, B.bz), block(B.tx, B.ty);
-#define BFLBM_LAUNCH_FUSED(PF, NT) \
-  k_step_fused<NOISE, PF, NT><<<grid, block, fused_smem_bytes(B), h->stream>>>(h->G, B, h->dp, h->step, h->X[h->cur], h->X[1 - h->cur], h->R, h->E)
-  if (B.tx * B.ty == 128) { if (h->prefetch) BFLBM_LAUNCH_FUSED(true, 128); else BFLBM_LAUNCH_FUSED(false, 128); }
-  else                    { if (h->prefetch) BFLBM_LAUNCH_FUSED(true, 256); else BFLBM_LAUNCH_FUSED(false, 256); }
-#undef BFLBM_LAUNCH_FUSED
+  const dim3 grid(B.bx, B.by, B.bz), block(B.tx, B.ty);
+  const double2* Ein = (h->e_valid && h->fold_in_staging) ? h->E[h->ecur] : nullptr;
+  double2* Eout = h->E[1 - h->ecur];
+  const PopBases XB = make_pop_bases(h->G, h->X[h->cur], h->X[1 - h->cur]);
+  if (B.tx * B.ty == 128)
+    k_step_fused<NOISE, R1, FU, 128><<<grid, block, fused_smem_bytes(B, R1), h->stream>>>(h->G, B, h->dp, h->step, XB, h->R, Ein, Eout);
+  else
+    k_step_fused<NOISE, R1, FU, 256><<<grid, block, fused_smem_bytes(B, R1), h->stream>>>(h->G, B, h->dp, h->step, XB, h->R, Ein, Eout);
   ++h->launches;
   CU(cudaGetLastError());
   return 0;
+}
+template <bool NOISE>
+int launch_fused(bflbm_lattice* h) {
+  const bool rate1 = h->rate1_fast_path && h->dp.rate_f == 1. && h->dp.rate_g == 1.;
+  const bool full = h->G.nx % h->B.tx == 0 && h->G.ny % h->B.ty == 0;
+  if (rate1) return full ? launch_fused_v<NOISE, true, true>(h) : launch_fused_v<NOISE, true, false>(h);
+  return full ? launch_fused_v<NOISE, false, true>(h) : launch_fused_v<NOISE, false, false>(h);
 }
 
 // collide+stream of the slab and local density partials; leaves the outgoing messages packed
 int step_local(bflbm_lattice* h) {
   const bool noise = h->prm.kBT > 0.;
   mark(h, 0);
+  int rc0 = 0;
+  // every kernel but the default one stages all planes from R; the default one only when E is not usable
+  if ((h->algo != 0 || !h->e_valid || !h->fold_in_staging) && (rc0 = ensure_full_R(h))) return rc0;
   if (h->algo == 1) {
+    h->e_valid = false;
     if (noise) k_step_twopass<true><<<cell_grid(h, h->G.nzl), h->block, 0, h->stream>>>(h->G, h->dp, h->step, h->X[h->cur], h->X[1 - h->cur], h->R);
     else       k_step_twopass<false><<<cell_grid(h, h->G.nzl), h->block, 0, h->stream>>>(h->G, h->dp, h->step, h->X[h->cur], h->X[1 - h->cur], h->R);
     ++h->launches;
@@ -343,8 +367,13 @@ int step_local(bflbm_lattice* h) {
   int rc = noise ? launch_fused<true>(h) : launch_fused<false>(h);
   if (rc) return rc;
   h->cur ^= 1;
+  h->ecur ^= 1;
   mark(h, 1);
-  if ((rc = fold_local(h))) return rc;
+  // the default kernel folds the brick-interior planes itself while staging (next step): only the brick faces here
+  const bool partial = h->algo == 0 && h->fold_in_staging && fold_in_staging_ok(h->G, h->B);
+  h->e_valid = partial;
+  h->r_stale = partial;
+  if ((rc = fold_local(h, partial ? 1 : 0))) return rc;
   mark(h, 2);
   rc = pack_halo(h);
   mark(h, 3);
@@ -403,7 +432,12 @@ int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, 
     h->cta_threads = (nt && atoi(nt) == 128) ? 128 : 256;
   }
   h->B = make_brick_grid(G, 0, h->cta_threads, 32);
-  TRY(dev_alloc(h, &h->E, brick_doubles2(h->B)));
+  TRY(dev_alloc(h, &h->E[0], brick_doubles2(h->B)));
+  TRY(dev_alloc(h, &h->E[1], brick_doubles2(h->B)));
+  {
+    const char* fs = getenv("BFLBM_FOLD_IN_STAGING");
+    h->fold_in_staging = !(fs && fs[0] == '0');
+  }
   h->halo_doubles = (size_t)14 * G.plane;
   for (int s = 0; s < 2; ++s) {
     TRY(dev_alloc(h, &h->send[s], h->halo_doubles));
@@ -413,8 +447,8 @@ int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, 
   TRY(dev_alloc(h, &h->diag_partial, h->diag_blocks * 5));
   TRY(dev_alloc(h, &h->diag_count, (size_t)1));
   {
-    const char* pf = getenv("BFLBM_PREFETCH");
-    h->prefetch = pf && pf[0] == '1';
+    const char* r1 = getenv("BFLBM_RATE1");
+    h->rate1_fast_path = !(r1 && r1[0] == '0');
     cudaError_t e = set_fused_smem(h->B);
     if (e != cudaSuccess) { bflbm_destroy(h); return fail(BFLBM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
   }
@@ -427,6 +461,8 @@ int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, 
 int finish_init(bflbm_lattice* h) {
   h->step = h->prm.step0;
   h->initialized = true;
+  h->e_valid = false;  // R was (or is about to be) rebuilt from the populations; E is void
+  h->r_stale = false;
   return 0;
 }
 
@@ -447,6 +483,7 @@ int observe(bflbm_lattice* h, int ncomp, double* out, bool out_is_device, bool c
   if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
   int rc = set_device(h);
   if (rc) return rc;
+  if ((rc = ensure_full_R(h))) return rc;
   const Geom& G = h->G;
   const bool noise = h->prm.kBT > 0.;
   const int cp = chunk_planes(h, ncomp, 0);
@@ -520,7 +557,7 @@ int bflbm_destroy(bflbm_lattice* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->X[0]); cudaFree(h->X[1]); cudaFree(h->R); cudaFree(h->E);
+  cudaFree(h->X[0]); cudaFree(h->X[1]); cudaFree(h->R); cudaFree(h->E[0]); cudaFree(h->E[1]);
   for (int s = 0; s < 2; ++s) { cudaFree(h->send[s]); cudaFree(h->recv[s]); }
   cudaFree(h->stage); cudaFree(h->diag_partial); cudaFree(h->diag_count);
   for (int i = 0; i < 5; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -560,7 +597,7 @@ int bflbm_set_stream(bflbm_lattice* h, void* s) {
 }
 int bflbm_set_algorithm(bflbm_lattice* h, int algo) {
   CHECK_H(h);
-  if (algo < 0 || algo > 2) return fail(BFLBM_ERR_ARG, "algorithm must be 0 (fused), 1 (two-pass) or 2 (fused, two threads per cell)");
+  if (algo < 0 || algo > 1) return fail(BFLBM_ERR_ARG, "algorithm must be 0 (fused one-pass) or 1 (two-pass)");
   if (algo == 1 && !h->whole_box) return fail(BFLBM_ERR_ARG, "the two-pass algorithm supports whole-box lattices only");
   h->algo = algo;
   return bflbm_set_tiling(h, h->lz_request);  // the brick shape depends on the kernel
@@ -573,12 +610,17 @@ int bflbm_set_tiling(bflbm_lattice* h, int brick_lz) {
   int rc = set_device(h);
   if (rc) return rc;
   CU(cudaStreamSynchronize(h->stream));
-  const BrickGrid nb = h->algo == 2 ? make_brick_grid(h->G, brick_lz, 128, 16) : make_brick_grid(h->G, brick_lz, h->cta_threads, 32);
+  if (h->initialized && (rc = ensure_full_R(h))) return rc;  // E is about to change shape: R takes over
+  CU(cudaStreamSynchronize(h->stream));
+  h->e_valid = false;
+  const BrickGrid nb = make_brick_grid(h->G, brick_lz, h->cta_threads, 32);
   if (brick_doubles2(nb) != brick_doubles2(h->B)) {
-    CU(cudaFree(h->E));
-    h->bytes -= brick_doubles2(h->B) * sizeof(double2);
-    h->E = nullptr;
-    if ((rc = dev_alloc(h, &h->E, brick_doubles2(nb)))) return rc;
+    for (int k = 0; k < 2; ++k) {
+      CU(cudaFree(h->E[k]));
+      h->bytes -= brick_doubles2(h->B) * sizeof(double2);
+      h->E[k] = nullptr;
+      if ((rc = dev_alloc(h, &h->E[k], brick_doubles2(nb)))) return rc;
+    }
   }
   h->B = nb;
   CU(set_fused_smem(nb));
@@ -678,6 +720,8 @@ int bflbm_halo_refresh_begin(bflbm_lattice* h) {
   if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
   int rc = set_device(h);
   if (rc) return rc;
+  h->e_valid = false;  // R is rebuilt from the populations below
+  h->r_stale = false;
   // local density partials straight from the populations: P = sum over owned source planes only
   k_density_partial<<<cell_grid(h, h->G.nzl + 2), h->block, 0, h->stream>>>(h->G, h->X[h->cur], h->R);
   ++h->launches;
@@ -711,6 +755,7 @@ int bflbm_get_populations(bflbm_lattice* h, double* f, double* g) {
   if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
   int rc = set_device(h);
   if (rc) return rc;
+  if ((rc = ensure_full_R(h))) return rc;
   const Geom& G = h->G;
   const int cp = chunk_planes(h, 2 * Q, 0);
   if ((rc = ensure_stage(h, (size_t)(2 * Q) * cp * G.plane))) return rc;
@@ -733,6 +778,7 @@ int bflbm_get_populations_device(bflbm_lattice* h, double* dev_f, double* dev_g)
   if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
   int rc = set_device(h);
   if (rc) return rc;
+  if ((rc = ensure_full_R(h))) return rc;
   const Geom& G = h->G;
   const int cp = chunk_planes(h, 2 * Q, 0);
   if ((rc = ensure_stage(h, (size_t)(2 * Q) * cp * G.plane))) return rc;
@@ -770,6 +816,7 @@ int bflbm_get_normals(bflbm_lattice* h, double* out33) { return observe<OBS_NORM
 static int run_diag(bflbm_lattice* h, double sums[5], unsigned long long* bad) {
   int rc = set_device(h);
   if (rc) return rc;
+  if ((rc = ensure_full_R(h))) return rc;
   CU(cudaMemsetAsync(h->diag_count, 0, sizeof(unsigned long long), h->stream));
   k_diag<<<cell_grid(h, h->G.nzl), h->block, 0, h->stream>>>(h->G, h->R, h->diag_partial, h->diag_count);
   ++h->launches;
@@ -810,6 +857,7 @@ int bflbm_check_nan(bflbm_lattice* h, long long* count) {
   if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
   int rc = set_device(h);
   if (rc) return rc;
+  if ((rc = ensure_full_R(h))) return rc;
   const Geom& G = h->G;
   const bool noise = h->prm.kBT > 0.;
   const int cp = chunk_planes(h, BFLBM_NHYDRO, 0);

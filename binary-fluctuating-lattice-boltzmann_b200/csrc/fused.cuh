@@ -52,9 +52,45 @@ inline BrickGrid make_brick_grid(const Geom& G, int lz_request = 0, int nthreads
   B.brick = (long long)B.pl * (lz + 2);
   return B;
 }
-inline size_t fused2_smem_bytes(const BrickGrid& B) { return (size_t)6 * B.pl * sizeof(double2); }
 inline size_t brick_doubles2(const BrickGrid& B) { return (size_t)B.brick * B.bx * B.by * B.bz; }
-inline size_t fused_smem_bytes(const BrickGrid& B) { return (size_t)6 * B.pl * sizeof(double2) + (size_t)15 * B.tx * B.ty * sizeof(double); }
+constexpr int FIX_SLOTS = 200;  // extra contributions of one extended plane: 2*(ex + ey) + 4*12 - ... <= 192 for ex*ey <= 2*NT
+inline size_t fused_smem_bytes(const BrickGrid& B, bool rate1) {
+  return (size_t)7 * B.pl * sizeof(double2) + (size_t)B.pl * sizeof(int4) + (size_t)FIX_SLOTS * sizeof(double2) +
+         (rate1 ? 0 : (size_t)15 * B.tx * B.ty * sizeof(double));
+}
+// fold-in-staging (the step kernel sums the brick contributions itself) needs every cell to lie in at most
+// 2 bricks per axis, i.e. no brick of width 1
+inline bool fold_in_staging_ok(const Geom& G, const BrickGrid& B) {
+  const int lx = G.nx - (B.bx - 1) * B.tx, ly = G.ny - (B.by - 1) * B.ty;  // width of the last (partial) brick
+  return lx >= 2 && ly >= 2 && B.pl <= 2 * B.tx * B.ty && (long long)B.by * B.bx * B.brick < 2147483647ll;
+}
+
+// Bricks whose extended box contains the column (gx, gy), in the canonical summation order
+// (dy: 0,-1,+1; dx: 0,-1,+1 relative to the brick that owns the column): c[dy][dx] = offset (in double2) of the
+// entry inside one brick row of E, or -1.  Used by k_fold and by the step kernel's staging table, so that both
+// add the same numbers in the same order.
+__device__ __forceinline__ void fold_candidates(const Geom& G, const BrickGrid& B, int gx, int gy, int (&c)[3][3]) {
+  int nbx[3], ncx[3], nby[3], ncy[3];
+  {
+    const int b = gx / B.tx, l = gx - b * B.tx, v = min(B.tx, G.nx - b * B.tx);
+    const int bm = (b + B.bx - 1) % B.bx, bp = (b + 1) % B.bx;
+    nbx[0] = b; ncx[0] = l + 1;
+    nbx[1] = (l == 0) ? bm : -1;     ncx[1] = min(B.tx, G.nx - bm * B.tx) + 1;
+    nbx[2] = (l == v - 1) ? bp : -1; ncx[2] = 0;
+  }
+  {
+    const int b = gy / B.ty, l = gy - b * B.ty, v = min(B.ty, G.ny - b * B.ty);
+    const int bm = (b + B.by - 1) % B.by, bp = (b + 1) % B.by;
+    nby[0] = b; ncy[0] = l + 1;
+    nby[1] = (l == 0) ? bm : -1;     ncy[1] = min(B.ty, G.ny - bm * B.ty) + 1;
+    nby[2] = (l == v - 1) ? bp : -1; ncy[2] = 0;
+  }
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx)
+      c[dy][dx] = (nby[dy] < 0 || nbx[dx] < 0) ? -1 : (nby[dy] * B.bx + nbx[dx]) * (int)B.brick + ncy[dy] * B.ex + ncx[dx];
+}
 
 // x-stage of the density scatter for one species.  p: post-collision populations of this thread's cell.
 // t[g]: what arrives in this thread's column for the 9 (cy,cz) groups (own cell + left neighbour's +x movers
@@ -85,32 +121,68 @@ __device__ __forceinline__ void scatter_x(const double (&p)[Q], int tx, int widt
 __device__ __forceinline__ double ld_off(const double* __restrict__ base, unsigned byte_off) {
   return __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + byte_off));
 }
-__device__ __forceinline__ void prefetch_l2(const double* __restrict__ base, unsigned byte_off) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + byte_off));
-}
 __device__ __forceinline__ void st_off(double* __restrict__ base, unsigned byte_off, double v) {
   *reinterpret_cast<double*>(reinterpret_cast<char*>(base) + byte_off) = v;
 }
 
-template <bool NOISE, bool PREFETCH, int NT>
+// asynchronous global->shared copies (SASS LDGSTS): the (rho,phi) plane needed two planes ahead is fetched at the
+// top of an iteration and lands while the current plane is collided (no registers, no exposed latency)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Base pointer of every population component, as a kernel parameter: the address of a load/store is then
+// (constant-bank 64-bit base) + (per-thread 32-bit offset) = IADD3 + IADD3.X, instead of a 64-bit multiply-add
+// by the component stride per access (4 instructions x 76 accesses per cell in the first version).
+struct PopBases {
+  const double* in[2 * Q];
+  double* out[2 * Q];
+};
+inline PopBases make_pop_bases(const Geom& G, const double* X, double* Xn) {
+  PopBases P;
+  for (int i = 0; i < 2 * Q; ++i) {
+    P.in[i] = X + (long long)i * G.comp;
+    P.out[i] = Xn + (long long)i * G.comp;
+  }
+  return P;
+}
+
+// RATE1: both relaxation rates are exactly 1 (tau_f = tau_g = 1/2, the reference's shipped and only documented
+// setting): the incoming non-conserved moments are not needed (see relax_species), nothing of species g is parked.
+// FULL: nx and ny are multiples of the tile, every thread owns a cell (no activity predicates, no divergence code).
+template <bool NOISE, bool RATE1, bool FULL, int NT>
 __global__ void __launch_bounds__(NT, 512 / NT)
-k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __restrict__ X, double* __restrict__ Xn,
-             const double2* __restrict__ R, double2* __restrict__ E) {
+k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B, const __grid_constant__ DevParams P, long long step,
+             const __grid_constant__ PopBases XB, const double2* __restrict__ R, const double2* __restrict__ Ein,
+             double2* __restrict__ E) {
   extern __shared__ double2 smem[];
-  double2* Rs = smem;             // [3][ey][ex] rolling (rho,phi) planes zl-1, zl, zl+1
-  double2* A = smem + 3 * B.pl;   // [3][ey][ex] rolling accumulators of next-step (rho,phi)
-  double* Sg = reinterpret_cast<double*>(smem + 6 * B.pl);  // [15][256] parked moments 4..18 of species g
+  double2* Rs = smem;             // [4][ey][ex] ring of (rho,phi) planes zl-1, zl, zl+1 and the one in flight (zl+2)
+  double2* A = smem + 4 * B.pl;   // [3][ey][ex] rolling accumulators of next-step (rho,phi)
+  int4* Tab = reinterpret_cast<int4*>(smem + 7 * B.pl);     // [ey][ex] fold table: 3 extra sources + meta per entry
+  double2* Fix = smem + 8 * B.pl;                           // [FIX_SLOTS] landing slots of the extra contributions
+  double* Sg = reinterpret_cast<double*>(Fix + FIX_SLOTS);  // [15][NT] parked moments 4..18 of species g (!RATE1)
+  __shared__ int nfix;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * B.tx + tx;
   const int x0 = blockIdx.x * B.tx, y0 = blockIdx.y * B.ty, zb = blockIdx.z * B.lz;
   const int x = x0 + tx, y = y0 + ty;
-  const bool active = x < G.nx && y < G.ny;
+  const bool active = FULL || (x < G.nx && y < G.ny);
   const int vz = min(B.lz, G.nzl - zb);
   double2* Eb = E + (((long long)blockIdx.z * B.by + blockIdx.y) * B.bx + blockIdx.x) * B.brick;
 
-  // stage one (rho,phi) plane zl (-1..nzl) of the tile + ring into slot s.  The in-plane source offsets are the
-  // same for every plane: computed once (each thread owns at most STG entries of the extended plane).
+  // Staging of one (rho,phi) plane zl (-1..nzl) of the tile + ring into ring slot s, two entries per thread.
+  //  - planes on a brick face in z (first / last plane of a brick, slab ghost planes) come from R, where k_fold
+  //    has already summed every contribution (and the halo exchange has merged the neighbour slab's);
+  //  - every other plane is FOLDED HERE from the previous step's extended boxes Ein: the own brick's extended
+  //    plane has the layout of the ring slot (one contiguous copy), and the entries that also lie in a neighbouring
+  //    brick's extended box (2 columns / rows on each face) fetch those 1 or 3 extra contributions into Fix[] and
+  //    add them in k_fold's canonical order.  No separate fold pass over the lattice, no R traffic for these planes.
+  // The in-plane source offsets are the same for every plane: computed once.
   constexpr int STG = 2;  // pl = (tx+2)(ty+2) <= 2*NT for every tile shape used (tx in 8..32, tx*ty = NT >= 128)
   int soff[STG];
+  if (tid == 0) nfix = 0;
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < STG; ++j) {
     const int idx = tid + j * NT;
@@ -119,21 +191,99 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
     gx = gx < 0 ? gx + G.nx : gx;
     gy = gy < 0 ? gy + G.ny : gy;
     soff[j] = idx < B.pl ? gy * G.nx + gx : -1;
-  }
-  auto stage_plane = [&](int zl, int s) {
-    const double2* Rp = R + (long long)(zl + 1) * G.plane;
+    if (Ein != nullptr && idx < B.pl) {
+      int4 t = make_int4(0, 0, 0, 0);
+      // entries beyond the ring of a partial tile are never read
+      if (exx <= min(B.tx, G.nx - x0) + 1 && ey <= min(B.ty, G.ny - y0) + 1) {
+        int c[3][3];
+        fold_candidates(G, B, gx, gy, c);
+        const int mine = ((int)blockIdx.y * B.bx + (int)blockIdx.x) * (int)B.brick + idx;
+        int ext[3] = {0, 0, 0}, n = 0, pos = 0, seen = 0;
 #pragma unroll
-    for (int j = 0; j < STG; ++j)
-      if (soff[j] >= 0) Rs[s * B.pl + tid + j * NT] = __ldg(Rp + soff[j]);
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const int o = c[dy][dx];
+            if (o < 0) continue;
+            if (o == mine) pos = seen;
+            else if (n < 3) ext[n++] = o;
+            ++seen;
+          }
+        if (n > 0) {
+          const int slot = atomicAdd(&nfix, n);
+          t = make_int4(ext[0], ext[1], ext[2], n | (pos << 4) | (slot << 8));
+        }
+      }
+      Tab[idx] = t;
+    }
+  }
+  const double2* Ein_row = Ein + (long long)blockIdx.z * B.by * B.bx * B.brick;                 // this brick row of Ein
+  const double2* Ein_own = Ein_row + ((long long)blockIdx.y * B.bx + blockIdx.x) * B.brick;    // this brick
+  auto from_R = [&](int zl) { const int l = zl - zb; return Ein == nullptr || l <= 0 || l >= vz - 1; };  // CTA-uniform
+  auto stage_plane = [&](int zl, int s) {
+    if (from_R(zl)) {
+      const double2* Rp = R + (long long)(zl + 1) * G.plane;
+#pragma unroll
+      for (int j = 0; j < STG; ++j)
+        if (soff[j] >= 0) cp_async16(Rs + s * B.pl + tid + j * NT, Rp + soff[j]);
+    } else {
+      const long long pz = (long long)(zl - zb + 1) * B.pl;  // extended plane of zl in every brick of this row
+#pragma unroll
+      for (int j = 0; j < STG; ++j) {
+        const int idx = tid + j * NT;
+        if (idx < B.pl) {
+          cp_async16(Rs + s * B.pl + idx, Ein_own + pz + idx);
+          const int4 t = Tab[idx];
+          const int n = t.w & 15, slot = t.w >> 8;
+          if (n > 0) cp_async16(Fix + slot, Ein_row + pz + t.x);
+          if (n > 1) {
+            cp_async16(Fix + slot + 1, Ein_row + pz + t.y);
+            cp_async16(Fix + slot + 2, Ein_row + pz + t.z);
+          }
+        }
+      }
+    }
+  };
+  // after cp_async_wait_all(): add the extra contributions of MY entries (their copies were all issued by me)
+  auto fold_plane = [&](int zl, int s) {
+    if (from_R(zl)) return;
+#pragma unroll
+    for (int j = 0; j < STG; ++j) {
+      const int idx = tid + j * NT;
+      if (idx < B.pl) {
+        const int4 t = Tab[idx];
+        const int n = t.w & 15, pos = (t.w >> 4) & 15, slot = t.w >> 8;
+        if (n > 0) {
+          const double2 own = Rs[s * B.pl + idx];
+          double2 v;
+          if (n == 1) {  // two addends: the order does not matter
+            const double2 e0 = Fix[slot];
+            v = make_double2(own.x + e0.x, own.y + e0.y);
+          } else {       // four addends: own goes to position pos of the canonical order
+            const double2 e0 = Fix[slot], e1 = Fix[slot + 1], e2 = Fix[slot + 2];
+            const double2 a0 = pos == 0 ? own : e0, a1 = pos == 0 ? e0 : (pos == 1 ? own : e1);
+            const double2 a2 = pos <= 1 ? e1 : (pos == 2 ? own : e2), a3 = pos == 3 ? own : e2;
+            v = make_double2(((a0.x + a1.x) + a2.x) + a3.x, ((a0.y + a1.y) + a2.y) + a3.y);
+          }
+          Rs[s * B.pl + idx] = v;
+        }
+      }
+    }
   };
   for (int idx = tid; idx < 3 * B.pl; idx += NT) A[idx] = make_double2(0., 0.);
+  __syncthreads();  // Tab is complete
   stage_plane(zb - 1, 0);
   stage_plane(zb, 1);
-  stage_plane(zb + 1, 2);
+  cp_async_commit();
+  cp_async_wait_all();
+  stage_plane(zb + 1, 2);  // the only prologue plane that can need Fix[]
+  cp_async_commit();
+  cp_async_wait_all();
+  fold_plane(zb + 1, 2);
   __syncthreads();
 
   const int cell = (ty + 1) * B.ex + (tx + 1);  // this thread's cell in an extended plane
-  // byte deltas to the periodic x-1 / x+1 and y-1 / y+1 neighbours (loop invariant); index 0: coordinate - 1 ... no:
+  // byte deltas to the periodic x-1 / x+1 and y-1 / y+1 neighbours (loop invariant):
   // dxv[0] = offset of x+1 minus offset of x (used when c_x = -1, source = x+1), dxv[1] = offset of x-1 minus x
   unsigned dxv[2], dyv[2], c_inpl;
   {
@@ -147,8 +297,12 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
   const unsigned pl8 = (unsigned)G.plane * 8u;
   for (int k = 0; k < vz; ++k) {
     const int zl = zb + k;
-    // slot of plane zl + d : (k + 1 + d) % 3
+    // ring slot of plane zl + d : (k + 1 + d) & 3 ; accumulator slot of plane zl + d : (k + 1 + d) % 3
+    const int r_m = k & 3, r_0 = (k + 1) & 3, r_p = (k + 2) & 3, r_n = (k + 3) & 3;
     const int s_m = k % 3, s_0 = (k + 1) % 3, s_p = (k + 2) % 3;
+    // plane zl+2 goes into the slot that held plane zl-2 (free since the barriers of the previous iteration)
+    if (zl + 2 <= G.nzl) stage_plane(zl + 2, r_n);
+    cp_async_commit();
     double tf[9], tg[9];
     double ef[5], eg[5];  // edge exports (left face on lane 0, right face on lane tx-1)
     const bool left = tx == 0;
@@ -163,7 +317,7 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
         {
           double nr[Q], np[Q];
           nr[0] = np[0] = 0.;
-          const int sl[3] = {s_m, s_0, s_p};
+          const int sl[3] = {r_m, r_0, r_p};
 #pragma unroll
           for (int i = 1; i < Q; ++i) {
             const double2 v = Rs[sl[1 + cz(i)] * B.pl + cell + cy(i) * B.ex + cx(i)];
@@ -187,27 +341,23 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
             off[i] = o;
           }
         }
-        if (PREFETCH && (tx & 15) == 0 && k + 1 < vz) {
-          // next plane of this column into L2 (one request per 128 B line) while this plane computes
-          const unsigned nxt = c + (unsigned)G.plane * 8u;
-#pragma unroll
-          for (int i = 0; i < 2 * Q; ++i) prefetch_l2(X + (long long)i * G.comp, nxt);
-        }
         {
           double f[Q];
           // species g first: its non-conserved moments wait in shared memory while species f is processed
 #pragma unroll
-          for (int i = 0; i < Q; ++i) f[i] = ld_off(X + (long long)(Q + i) * G.comp, off[i]);
+          for (int i = 0; i < Q; ++i) f[i] = ld_off(XB.in[Q + i], off[i]);
           moments(f, mg);
+          if (!RATE1) {
 #pragma unroll
-          for (int a = 4; a < Q; ++a) Sg[(a - 4) * NT + tid] = mg[a];
+            for (int a = 4; a < Q; ++a) Sg[(a - 4) * NT + tid] = mg[a];
+          }
 #pragma unroll
-          for (int i = 0; i < Q; ++i) f[i] = ld_off(X + (long long)i * G.comp, off[i]);
+          for (int i = 0; i < Q; ++i) f[i] = ld_off(XB.in[i], off[i]);
           moments(f, mf);
         }
         nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
         collide_prepare<NOISE>(P, grho, gphi, nk, mf, mg, C);
-        collide_species<NOISE, 0>(P, nk, C, mf);
+        collide_species<NOISE, 0, RATE1>(P, nk, C, mf);
       } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) mf[i] = 0.;
@@ -216,16 +366,18 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
       populations(mf, p);
       if (active) {
 #pragma unroll
-        for (int i = 0; i < Q; ++i) st_off(Xn + (long long)i * G.comp, c, p[i]);
+        for (int i = 0; i < Q; ++i) st_off(XB.out[i], c, p[i]);
       }
       scatter_x(p, tx, B.tx, tf);
       // what leaves through the left face (lane 0) / right face (lane tx-1); unused on the other lanes
       ef[0] = left ? p[2] : p[1]; ef[1] = left ? p[10] : p[7]; ef[2] = left ? p[8] : p[9];
       ef[3] = left ? p[18] : p[15]; ef[4] = left ? p[16] : p[17];
       if (active) {
+        if (!RATE1) {
 #pragma unroll
-        for (int a = 4; a < Q; ++a) mg[a] = Sg[(a - 4) * NT + tid];
-        collide_species<NOISE, 1>(P, nk, C, mg);
+          for (int a = 4; a < Q; ++a) mg[a] = Sg[(a - 4) * NT + tid];
+        }
+        collide_species<NOISE, 1, RATE1>(P, nk, C, mg);
       } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) mg[i] = 0.;
@@ -233,7 +385,7 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
       populations(mg, p);
       if (active) {
 #pragma unroll
-        for (int i = 0; i < Q; ++i) st_off(Xn + (long long)(Q + i) * G.comp, c, p[i]);
+        for (int i = 0; i < Q; ++i) st_off(XB.out[Q + i], c, p[i]);
       }
       scatter_x(p, tx, B.tx, tg);
       eg[0] = left ? p[2] : p[1]; eg[1] = left ? p[10] : p[7]; eg[2] = left ? p[8] : p[9];
@@ -243,8 +395,9 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
     const bool edge = (tx == 0) || (tx == B.tx - 1);
     const int ecell = (ty + 1) * B.ex + (tx == 0 ? 0 : B.tx + 1);
 
-    __syncthreads();  // S0: everyone is done reading Rs slot s_m (plane zl-1) and the last write-out is finished
-    if (zl + 2 <= G.nzl) stage_plane(zl + 2, s_m);
+    cp_async_wait_all();  // my part of plane zl+2 has landed; the barriers below publish it to the CTA
+    if (zl + 2 <= G.nzl) fold_plane(zl + 2, r_n);
+    __syncthreads();      // S0: the write-out of the previous iteration is finished
     auto add = [&](int slot, int at, double a, double b) {
       double2 v = A[slot * B.pl + at];
       v.x += a;
@@ -287,252 +440,69 @@ k_step_fused(Geom G, BrickGrid B, DevParams P, long long step, const double* __r
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Species-split variant of the fused step: TWO threads per cell, lane l (l < 16) handles species f and lane
-// l + 16 species g of the same cell (a warp = 16 consecutive cells x 2 species).  Each thread carries 19
-// instead of 38 populations, so the kernel fits 3 CTAs (24 warps) per SM instead of 16 warps, and the
-// per-warp critical path between barriers is half as long: the collision is latency/issue bound
-// (profiles/r1_*), not DRAM bound, and more resident warps is what it needs.
-// The code is species-uniform: the species enters only as data (base pointers, rate, sign of the momentum
-// noise, Philox block offset), so the two half-warps never diverge.  What each thread needs from the other
-// species (density, momentum, acceleration, real velocity) crosses with shfl.xor 16.
-
-// everything the relaxation of species s needs: own real velocity u, barycentric velocity vb, momentum noise xi
-template <bool NOISE>
-__device__ __forceinline__ void pair_hydro(const DevParams& P, int s, double dens_s, const double (&j_s)[3], const double (&a_s)[3],
-                                           const float (&n3)[3], double (&u_s)[3], double (&vb)[3], double (&xi_s)[3]) {
-  const unsigned full = 0xffffffffu;
-  const double dens_o = __shfl_xor_sync(full, dens_s, 16);
-  const bool has_s = fabs(dens_s) > (double)FLT_EPSILON;
-  const double inv_s = has_s ? 1. / dens_s : 0.;
-  const double inv_o = __shfl_xor_sync(full, inv_s, 16);
-  const double inv_tot = 1. / (dens_s + dens_o);  // unguarded like the reference; a+b is the same in both lanes
-  const double fric_s = s ? P.fric_g : P.fric_f;
-  double amp = 0.;
-  if (NOISE) amp = sqrt(P.amp_j * fabs(dens_s * dens_o * inv_tot));
-  const double sign = s ? -1. : 1.;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const double j_o = __shfl_xor_sync(full, j_s[k], 16), a_o = __shfl_xor_sync(full, a_s[k], 16);
-    const double ub_s = j_s[k] * inv_s, ub_o = j_o * inv_o;
-    xi_s[k] = NOISE ? sign * (amp * (double)n3[k]) : 0.;
-    const double d = (ub_s - ub_o) + 0.5 * (a_s[k] - a_o);
-    u_s[k] = ub_s + 0.5 * a_s[k] - fric_s * dens_o * inv_tot * d + 0.5 * (xi_s[k] * inv_s);
-    const double u_o = __shfl_xor_sync(full, u_s[k], 16);
-    // (rho u_f + phi u_g)/(rho+phi), LBM_binary.H:471; no fma contraction so that both lanes get the same bits
-    vb[k] = __dmul_rn(__dadd_rn(__dmul_rn(dens_s, u_s[k]), __dmul_rn(dens_o, u_o)), inv_tot);
-  }
-}
-
-template <bool NOISE>
-__global__ void __launch_bounds__(256, 3)
-k_step_fused2(Geom G, BrickGrid B, DevParams P, long long step, const double* __restrict__ X, double* __restrict__ Xn,
-              const double2* __restrict__ R, double2* __restrict__ E) {
-  constexpr int NT = 256;
-  extern __shared__ double2 smem[];
-  double2* Rs = smem;             // [3][ey][ex] rolling (rho,phi) planes zl-1, zl, zl+1
-  double2* A = smem + 3 * B.pl;   // [3][ey][ex] rolling accumulators of next-step (rho,phi)
-  double* Ad = reinterpret_cast<double*>(A);
-  const double* Rd = reinterpret_cast<const double*>(Rs);
-  const int tid = threadIdx.x, lane = tid & 31, s = lane >> 4;
-  const int cidx = (tid >> 5) * 16 + (lane & 15);  // cell of the tile (tx*ty = 128 cells)
-  const int tx = cidx % B.tx, ty = cidx / B.tx;
-  const int x0 = blockIdx.x * B.tx, y0 = blockIdx.y * B.ty, zb = blockIdx.z * B.lz;
-  const int x = x0 + tx, y = y0 + ty;
-  const bool active = x < G.nx && y < G.ny;
-  const int vz = min(B.lz, G.nzl - zb);
-  double2* Eb = E + (((long long)blockIdx.z * B.by + blockIdx.y) * B.bx + blockIdx.x) * B.brick;
-  const double* __restrict__ Xs = X + (long long)(s * Q) * G.comp;
-  double* __restrict__ Xns = Xn + (long long)(s * Q) * G.comp;
-
-  auto stage_plane = [&](int zl, int slot) {
-    const double2* Rp = R + (long long)(zl + 1) * G.plane;
-    for (int idx = tid; idx < B.pl; idx += NT) {
-      const int ey = idx / B.ex, exx = idx - ey * B.ex;
-      int gx = (x0 - 1 + exx) % G.nx, gy = (y0 - 1 + ey) % G.ny;
-      gx = gx < 0 ? gx + G.nx : gx;
-      gy = gy < 0 ? gy + G.ny : gy;
-      Rs[slot * B.pl + idx] = __ldg(Rp + (long long)gy * G.nx + gx);
-    }
-  };
-  for (int idx = tid; idx < 3 * B.pl; idx += NT) A[idx] = make_double2(0., 0.);
-  stage_plane(zb - 1, 0);
-  stage_plane(zb, 1);
-  stage_plane(zb + 1, 2);
-  __syncthreads();
-
-  // in-component byte offsets of the in-plane parts of the 19 pull sources (plane part added per plane)
-  const unsigned xs[3] = {(unsigned)(x == 0 ? G.nx - 1 : x - 1), (unsigned)min(x, G.nx - 1), (unsigned)(x >= G.nx - 1 ? 0 : x + 1)};
-  const int yc = min(y, G.ny - 1);
-  const unsigned yr[3] = {(unsigned)(yc == 0 ? G.ny - 1 : yc - 1) * (unsigned)G.nx, (unsigned)yc * (unsigned)G.nx,
-                          (unsigned)(yc == G.ny - 1 ? 0 : yc + 1) * (unsigned)G.nx};
-  const int cell = (ty + 1) * B.ex + (tx + 1);  // this thread's cell in an extended plane
-  const bool left = tx == 0, edge = left || tx == B.tx - 1;
-  const int ecell = (ty + 1) * B.ex + (left ? 0 : B.tx + 1);
-  const double rate = s ? P.rate_g : P.rate_f;
-
-  for (int k = 0; k < vz; ++k) {
-    const int zl = zb + k;
-    const int s_m = k % 3, s_0 = (k + 1) % 3, s_p = (k + 2) % 3;  // slot of plane zl + d : (k + 1 + d) % 3
-    double t[9], e[5];
-    {
-      // acceleration of this species from the gradient of the OTHER species' density (LBM_binary.H:134-150, 254-255)
-      double go[3];
-      {
-        double n[Q];
-        n[0] = 0.;
-        const int sl[3] = {s_m, s_0, s_p};
-#pragma unroll
-        for (int i = 1; i < Q; ++i) n[i] = Rd[2 * (sl[1 + cz(i)] * B.pl + cell + cy(i) * B.ex + cx(i)) + (1 - s)];
-        gradient19(n, go);
-      }
-      const unsigned pl8 = (unsigned)G.plane * 8u;
-      const unsigned zp[3] = {(unsigned)zl * pl8, (unsigned)(zl + 1) * pl8, (unsigned)(zl + 2) * pl8};
-      const unsigned c = zp[1] + (yr[1] + xs[1]) * 8u;
-      double m[Q];
-      {
-        double f[Q];
-#pragma unroll
-        for (int i = 0; i < Q; ++i) {
-          const unsigned off = zp[1 - cz(i)] + (yr[1 - cy(i)] + xs[1 - cx(i)]) * 8u;
-          f[i] = active ? ld_off(Xs + (long long)i * G.comp, off) : 0.;
-        }
-        moments(f, m);
-      }
-      const bool has_s = fabs(m[0]) > (double)FLT_EPSILON;
-      double a_s[3], u_s[3], vb[3], xi_s[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) a_s[d] = has_s ? P.acc_coef * go[d] : 0.;
-      NoiseKey nk;
-      float n0[4] = {0.f, 0.f, 0.f, 0.f};
-      if (NOISE) {
-        nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
-        normals4(nk, 0, n0);
-      }
-      {
-        const double j_s[3] = {m[1], m[2], m[3]};
-        const float n3[3] = {n0[0], n0[1], n0[2]};
-        pair_hydro<NOISE>(P, s, m[0], j_s, a_s, n3, u_s, vb, xi_s);
-      }
-      relax_species(rate, P.force_pf, m[0], vb, u_s, a_s, m);
-      if (NOISE) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) m[1 + d] += xi_s[d];
-        const double sa = sqrt(P.amp_s * fabs(m[0]));
-        float nb[4];
-#pragma unroll
-        for (int a = 4; a < Q; ++a) {
-          if (((a - 4) & 3) == 0) normals4(nk, 1 + 4 * s + ((a - 4) >> 2), nb);  // = mode_index(s, a) >> 2
-          m[a] += (sqrt_bnorm(a) * sa) * (double)nb[(a - 4) & 3];
-        }
-      }
-      double p[Q];
-      populations(m, p);
-      if (active) {
-#pragma unroll
-        for (int i = 0; i < Q; ++i) st_off(Xns + (long long)i * G.comp, c, p[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < Q; ++i) p[i] = 0.;
-      }
-      scatter_x(p, tx, B.tx, t);
-      // what leaves through the left face (lane 0) / right face (lane tx-1); unused on the other lanes
-      e[0] = left ? p[2] : p[1]; e[1] = left ? p[10] : p[7]; e[2] = left ? p[8] : p[9];
-      e[3] = left ? p[18] : p[15]; e[4] = left ? p[16] : p[17];
-    }
-
-    __syncthreads();  // S0: everyone is done reading Rs slot s_m (plane zl-1) and the last write-out is finished
-    if (zl + 2 <= G.nzl) stage_plane(zl + 2, s_m);
-    auto add = [&](int slot, int at, double v) { Ad[2 * (slot * B.pl + at) + s] += v; };
-    // phase cy = 0 : own row.  groups 0 (cz 0), 3 (cz +1), 4 (cz -1)
-    add(s_0, cell, t[0]);
-    add(s_p, cell, t[3]);
-    add(s_m, cell, t[4]);
-    if (edge) {
-      add(s_0, ecell, e[0]);
-      add(s_p, ecell, e[3]);
-      add(s_m, ecell, e[4]);
-    }
-    __syncthreads();
-    // phase cy = +1 : row above.  groups 1 (cz 0), 5 (cz +1), 7 (cz -1)
-    add(s_0, cell + B.ex, t[1]);
-    add(s_p, cell + B.ex, t[5]);
-    add(s_m, cell + B.ex, t[7]);
-    if (edge) add(s_0, ecell + B.ex, e[1]);
-    __syncthreads();
-    // phase cy = -1 : row below.  groups 2 (cz 0), 8 (cz +1), 6 (cz -1)
-    add(s_0, cell - B.ex, t[2]);
-    add(s_p, cell - B.ex, t[8]);
-    add(s_m, cell - B.ex, t[6]);
-    if (edge) add(s_0, ecell - B.ex, e[2]);
-    __syncthreads();
-    // plane zl-1 has received everything this brick can give it: write it out (extended plane k) and recycle
-    for (int idx = tid; idx < B.pl; idx += NT) {
-      Eb[(long long)k * B.pl + idx] = A[s_m * B.pl + idx];
-      A[s_m * B.pl + idx] = make_double2(0., 0.);
-    }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < B.pl; idx += NT) {
-    Eb[(long long)vz * B.pl + idx] = A[(vz % 3) * B.pl + idx];
-    Eb[(long long)(vz + 1) * B.pl + idx] = A[((vz + 1) % 3) * B.pl + idx];
-  }
-}
-
 // (rho,phi)(x,y,zl) = sum over the bricks whose extended box contains the cell, fixed order
 // (dz: 0,-1,+1; dy: 0,-1,+1; dx: 0,-1,+1), grouped per dz so that the part a neighbouring slab contributes
 // (dz = -1 at the bottom plane, +1 at the top plane) is ONE addend: bit-identical for any slab count.
 // zl = -1 and zl = nzl give this slab's contribution to the neighbour's boundary plane.
-__global__ void __launch_bounds__(256) k_fold(Geom G, BrickGrid B, const double2* __restrict__ E, double2* __restrict__ R) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zl = (int)blockIdx.z - 1;
+// Launched brick-wise like the step kernel (grid = bricks, thread = column, loop over the brick's planes): the
+// in-plane candidate list of a column is loop invariant, so a plane costs a handful of predicated 16-byte loads and
+// no integer division (the first, cell-per-thread version spent ~250 instructions per cell and ran at 2.6 TB/s).
+// MODE 0: every plane.  MODE 1: only what the step kernel does not fold itself -- the first and last plane of every
+// brick and the two slab-face outputs (zl = -1, nzl).  MODE 2: the complement of MODE 1 (on demand, for the observers).
+template <int MODE>
+__global__ void __launch_bounds__(256, 4) k_fold(Geom G, BrickGrid B, const double2* __restrict__ E, double2* __restrict__ R) {
+  const int bX = blockIdx.x, bY = blockIdx.y, bZ = blockIdx.z;
+  const int lx = threadIdx.x, ly = threadIdx.y;
+  const int x = bX * B.tx + lx, y = bY * B.ty + ly;
   if (x >= G.nx || y >= G.ny) return;
-  int nbx[3], ncx[3], nby[3], ncy[3], nbz[3], ncz[3];  // candidate (brick, extended coordinate) per axis; brick -1 = none
-  {
-    const int b = x / B.tx, l = x - b * B.tx, v = min(B.tx, G.nx - b * B.tx);
-    const int bm = (b + B.bx - 1) % B.bx, bp = (b + 1) % B.bx;
-    nbx[0] = b; ncx[0] = l + 1;
-    nbx[1] = (l == 0) ? bm : -1;     ncx[1] = min(B.tx, G.nx - bm * B.tx) + 1;
-    nbx[2] = (l == v - 1) ? bp : -1; ncx[2] = 0;
-  }
-  {
-    const int b = y / B.ty, l = y - b * B.ty, v = min(B.ty, G.ny - b * B.ty);
-    const int bm = (b + B.by - 1) % B.by, bp = (b + 1) % B.by;
-    nby[0] = b; ncy[0] = l + 1;
-    nby[1] = (l == 0) ? bm : -1;     ncy[1] = min(B.ty, G.ny - bm * B.ty) + 1;
-    nby[2] = (l == v - 1) ? bp : -1; ncy[2] = 0;
-  }
-  if (zl < 0) {
-    nbz[0] = -1; ncz[0] = 0; nbz[1] = -1; ncz[1] = 0; nbz[2] = 0; ncz[2] = 0;
-  } else if (zl >= G.nzl) {
-    nbz[0] = -1; ncz[0] = 0; nbz[2] = -1; ncz[2] = 0;
-    nbz[1] = B.bz - 1; ncz[1] = min(B.lz, G.nzl - (B.bz - 1) * B.lz) + 1;
-  } else {
-    const int b = zl / B.lz, l = zl - b * B.lz, v = min(B.lz, G.nzl - b * B.lz);
-    nbz[0] = b; ncz[0] = l + 1;
-    nbz[1] = (l == 0 && b > 0) ? b - 1 : -1;            ncz[1] = B.lz + 1;  // a lower brick is always full height
-    nbz[2] = (l == v - 1 && b + 1 < B.bz) ? b + 1 : -1; ncz[2] = 0;
-  }
-  double2 tot = make_double2(0., 0.);
-  bool tot_set = false;
+  int inpl[3][3];
+  fold_candidates(G, B, x, y, inpl);
+  const long long zrow = (long long)B.by * B.bx * B.brick;  // E stride between brick rows in z
+  // sum over the in-plane candidates of extended plane ez of brick row bz
+  auto group = [&](int bz, int ez) {
+    const double2* Ez = E + bz * zrow + (long long)ez * B.pl;
+    double2 s = __ldg(Ez + inpl[0][0]);  // the own brick always contains the cell
 #pragma unroll
-  for (int dz = 0; dz < 3; ++dz) {
-    if (nbz[dz] < 0) continue;
-    double2 s = make_double2(0., 0.);
-    bool s_set = false;
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      if (nby[dy] < 0) continue;
+    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        if (nbx[dx] < 0) continue;
-        const long long brick = ((long long)nbz[dz] * B.by + nby[dy]) * B.bx + nbx[dx];
-        const double2 v = __ldg(E + brick * B.brick + (long long)ncz[dz] * B.pl + ncy[dy] * B.ex + ncx[dx]);
-        if (s_set) { s.x += v.x; s.y += v.y; } else { s = v; s_set = true; }
+        if (dy == 0 && dx == 0) continue;
+        if (inpl[dy][dx] >= 0) {
+          const double2 v = __ldg(Ez + inpl[dy][dx]);
+          s.x += v.x;
+          s.y += v.y;
+        }
       }
-    }
-    if (tot_set) { tot.x += s.x; tot.y += s.y; } else { tot = s; tot_set = true; }
+    return s;
+  };
+  const int zb = bZ * B.lz, vz = min(B.lz, G.nzl - zb);
+  double2* Rc = R + (long long)y * G.nx + x;
+  if (MODE != 2) {
+    if (bZ == 0) Rc[0] = group(0, 0);  // zl = -1 : what this slab gives to the lower neighbour's boundary plane
+    if (bZ == B.bz - 1) Rc[(long long)(G.nzl + 1) * G.plane] = group(bZ, vz + 1);  // zl = nzl
   }
-  R[(long long)(zl + 1) * G.plane + (long long)y * G.nx + x] = tot;
+  auto plane = [&](int l) {
+    double2 tot = group(bZ, l + 1);
+    if (l == 0 && bZ > 0) {  // a lower brick is always full height
+      const double2 s = group(bZ - 1, B.lz + 1);
+      tot.x += s.x;
+      tot.y += s.y;
+    }
+    if (l == vz - 1 && bZ + 1 < B.bz) {
+      const double2 s = group(bZ + 1, 0);
+      tot.x += s.x;
+      tot.y += s.y;
+    }
+    Rc[(long long)(zb + l + 1) * G.plane] = tot;
+  };
+  if (MODE == 1) {
+    plane(0);
+    if (vz > 1) plane(vz - 1);
+  } else {
+    const int lo = MODE == 2 ? 1 : 0, hi = MODE == 2 ? vz - 1 : vz;
+#pragma unroll 4
+    for (int l = lo; l < hi; ++l) plane(l);
+  }
 }
 
 // same local sums straight from the populations (after a restart upload, before the first fused step):

@@ -69,26 +69,31 @@ __device__ __forceinline__ void cell_hydro(const DevParams& P, double rho, doubl
 }
 
 // m <- m + rate (meq(D, vb) - m) + Phi(D, u, a)   for one species (noise is added separately)
+// RATE1: the relaxation rate 1/(tau + 1/2) is exactly 1 (the reference's shipped tau = 1/2, LBM_binary.H:18-19):
+// every mode is reset to equilibrium + force, so the incoming non-conserved moments m[4..18] are never read and
+// the caller's forward transform shrinks to the conserved moments (dead-code elimination does the rest).
+template <bool RATE1 = false>
 __device__ __forceinline__ void relax_species(double rate, double pf, double D, const double (&vb)[3], const double (&u)[3],
                                               const double (&a)[3], double (&m)[Q]) {
   const double keep = 1. - rate;
-  const double Dr = D * rate, Dp = D * pf;
+  const double Dr = RATE1 ? D : D * rate, Dp = D * pf;
+  auto upd = [&](int k, double v) { m[k] = RATE1 ? v : keep * m[k] + v; };
   // momentum modes
 #pragma unroll
-  for (int k = 0; k < 3; ++k) m[1 + k] = keep * m[1 + k] + Dr * vb[k] + Dp * a[k];
+  for (int k = 0; k < 3; ++k) upd(1 + k, Dr * vb[k] + Dp * a[k]);
   // stress modes
   const double vxx = vb[0] * vb[0], vyy = vb[1] * vb[1], vzz = vb[2] * vb[2];
   const double axx = a[0] * u[0], ayy = a[1] * u[1], azz = a[2] * u[2];
   const double tr = axx + ayy + azz;
-  m[4] = keep * m[4] + Dr * (vxx + vyy + vzz) + Dp * (2. * tr);
-  m[5] = keep * m[5] + Dr * (2. * vxx - vyy - vzz) + Dp * (6. * axx - 2. * tr);
-  m[6] = keep * m[6] + Dr * (vyy - vzz) + Dp * (2. * (ayy - azz));
-  m[7] = keep * m[7] + Dr * (vb[0] * vb[1]) + Dp * (a[0] * u[1] + a[1] * u[0]);
-  m[8] = keep * m[8] + Dr * (vb[1] * vb[2]) + Dp * (a[1] * u[2] + a[2] * u[1]);
-  m[9] = keep * m[9] + Dr * (vb[0] * vb[2]) + Dp * (a[0] * u[2] + a[2] * u[0]);
+  upd(4, Dr * (vxx + vyy + vzz) + Dp * (2. * tr));
+  upd(5, Dr * (2. * vxx - vyy - vzz) + Dp * (6. * axx - 2. * tr));
+  upd(6, Dr * (vyy - vzz) + Dp * (2. * (ayy - azz)));
+  upd(7, Dr * (vb[0] * vb[1]) + Dp * (a[0] * u[1] + a[1] * u[0]));
+  upd(8, Dr * (vb[1] * vb[2]) + Dp * (a[1] * u[2] + a[2] * u[1]));
+  upd(9, Dr * (vb[0] * vb[2]) + Dp * (a[0] * u[2] + a[2] * u[0]));
   // ghost modes: no equilibrium, no force
 #pragma unroll
-  for (int k = 10; k < Q; ++k) m[k] = keep * m[k];
+  for (int k = 10; k < Q; ++k) upd(k, 0.);
 }
 
 // Collision of one cell in moment space, split in three so that the caller can finish species f (inverse
@@ -103,8 +108,8 @@ struct CollideCtx {
 template <bool NOISE>
 __device__ __forceinline__ void collide_prepare(const DevParams& P, const double (&grad_rho)[3], const double (&grad_phi)[3],
                                                 const NoiseKey& nk, const double (&mf)[Q], const double (&mg)[Q], CollideCtx& C) {
-  float n0[4] = {0.f, 0.f, 0.f, 0.f};
-  if (NOISE) normals4(nk, 0, n0);
+  float n0[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (NOISE) species_normals<0, 0, 4>(nk, n0);
   const float n3[3] = {n0[0], n0[1], n0[2]};
   const double jf[3] = {mf[1], mf[2], mf[3]}, jg[3] = {mg[1], mg[2], mg[3]};
   cell_hydro<NOISE>(P, mf[0], mg[0], jf, jg, grad_rho, grad_phi, n3, C.H);
@@ -113,36 +118,37 @@ __device__ __forceinline__ void collide_prepare(const DevParams& P, const double
 }
 
 // SPECIES 0 = f (call first), 1 = g
-template <bool NOISE, int SPECIES>
+template <bool NOISE, int SPECIES, bool RATE1 = false>
 __device__ __forceinline__ void collide_species(const DevParams& P, const NoiseKey& nk, CollideCtx& C, double (&m)[Q]) {
   const CellHydro& H = C.H;
-  if (SPECIES == 0) relax_species(P.rate_f, P.force_pf, H.rho, C.vb, H.uf, H.af, m);
-  else              relax_species(P.rate_g, P.force_pf, H.phi, C.vb, H.ug, H.ag, m);
+  if (SPECIES == 0) relax_species<RATE1>(P.rate_f, P.force_pf, H.rho, C.vb, H.uf, H.af, m);
+  else              relax_species<RATE1>(P.rate_g, P.force_pf, H.phi, C.vb, H.ug, H.ag, m);
   if (NOISE) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) m[1 + k] += (SPECIES == 0 ? H.xi[k] : -H.xi[k]);
     const double s = sqrt(P.amp_s * fabs(SPECIES == 0 ? H.rho : H.phi));
-    float nb[4];
+    // modes 4..18 : normals F[3..17] (the pair F[2], F[3] is recomputed from block 0, already live) / G[0..14]
+    constexpr int LO = SPECIES == 0 ? 2 : 0, HI = SPECIES == 0 ? 18 : 15;
+    float nb[HI - LO + 1];
+    species_normals<SPECIES, LO, HI>(nk, nb);
 #pragma unroll
-    for (int a = 4; a < Q; ++a) {
-      const int j = mode_index(SPECIES, a);
-      if ((j & 3) == 0) normals4(nk, j >> 2, nb);
-      m[a] += (sqrt_bnorm(a) * s) * (double)nb[j & 3];
-    }
+    for (int a = 4; a < Q; ++a) m[a] += (sqrt_bnorm(a) * s) * (double)nb[mode_index(SPECIES, a) - LO];
   }
 }
 
-// the 33 standard normals of a cell in REFERENCE draw order (observer / test hook)
+// the 33 standard normals of a cell in REFERENCE draw order (LBM_binary.H:115-127: a = 1..3 one draw each,
+// a = 4..18 two draws each, f then g) -- observer / test hook
 __device__ __forceinline__ void cell_normals(const NoiseKey& nk, float (&n)[36]) {
-  float raw[36];
+  float F[19], G[16];
+  species_normals<0, 0, 18>(nk, F);
+  species_normals<1, 0, 15>(nk, G);
 #pragma unroll
-  for (int b = 0; b < 9; ++b) {
-    float t[4];
-    normals4(nk, b, t);
-    raw[4 * b] = t[0]; raw[4 * b + 1] = t[1]; raw[4 * b + 2] = t[2]; raw[4 * b + 3] = t[3];
+  for (int d = 0; d < 3; ++d) n[d] = F[d];
+#pragma unroll
+  for (int a = 4; a < Q; ++a) {
+    n[3 + 2 * (a - 4)] = F[mode_index(0, a)];
+    n[4 + 2 * (a - 4)] = G[mode_index(1, a)];
   }
-#pragma unroll
-  for (int d = 0; d < 33; ++d) n[d] = raw[draw_index(d)];
   n[33] = n[34] = n[35] = 0.f;
 }
 

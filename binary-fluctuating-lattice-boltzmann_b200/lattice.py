@@ -186,7 +186,7 @@ class Lattice:
         _check(self.lib.bflbm_set_stream(self.h, ctypes.c_void_p(cuda_stream or 0)))
 
     def set_algorithm(self, name: str):
-        _check(self.lib.bflbm_set_algorithm(self.h, {"fused": 0, "twopass": 1, "fused2": 2}[name]))
+        _check(self.lib.bflbm_set_algorithm(self.h, {"fused": 0, "twopass": 1}[name]))
 
     def set_tiling(self, lz: int):
         _check(self.lib.bflbm_set_tiling(self.h, int(lz)))
