@@ -62,7 +62,7 @@ def load_library() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("BFLBM_LIB") or _build.LIB  # BFLBM_LIB: A/B runs of two builds of the same library
     if not os.path.exists(path):
         raise BflbmError(f"CUDA library {path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                          "(there is no CPU fallback)")
