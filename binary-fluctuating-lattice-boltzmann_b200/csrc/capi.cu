@@ -55,6 +55,12 @@ struct bflbm_lattice {
 
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // slab step with the halo exchange overlapped: the first and last brick row, the slab-face fold and the packing run
+  // on `stream` (where the caller then queues its NCCL send/recv); the interior rows run on `aux` meanwhile
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_prev = nullptr, ev_ends = nullptr, ev_interior = nullptr;
+  bool overlap = true;          // BFLBM_OVERLAP=0: everything on `stream`, exchange after the whole step kernel
+  bool interior_pending = false;
 
   double* X[2] = {nullptr, nullptr};
   int cur = 0;
@@ -179,9 +185,9 @@ int ensure_stage(bflbm_lattice* h, size_t doubles) {
   return 0;
 }
 
-// planes per chunk so that ncomp*planes*plane doubles stay below ~256 MiB
+// planes per chunk so that ncomp*planes*plane doubles stay below 1 GiB
 int chunk_planes(const bflbm_lattice* h, int ncomp, int extra_planes) {
-  const size_t budget = (size_t)32 << 20;  // doubles
+  const size_t budget = (size_t)128 << 20;  // doubles (1 GiB stage)
   long long per_plane = (long long)ncomp * h->G.plane;
   long long n = (long long)(budget / (size_t)per_plane) - extra_planes;
   if (n < 1) n = 1;
@@ -305,12 +311,16 @@ int unpack_halo(bflbm_lattice* h, double* const recv[2]) {
 }
 
 // mode 0: all planes; 1: brick-face planes + slab-face outputs; 2: the complement of 1
-int fold_local(bflbm_lattice* h, int mode) {
+// 3: the four slab-face planes (first / last brick row only); 4 = 1 without 3
+int fold_local(bflbm_lattice* h, int mode, cudaStream_t st = nullptr) {
   const Geom& G = h->G;
-  const dim3 grid(h->B.bx, h->B.by, h->B.bz), block(h->B.tx, h->B.ty);
-  if (mode == 0)      k_fold<0><<<grid, block, 0, h->stream>>>(G, h->B, h->E[h->ecur], h->R);
-  else if (mode == 1) k_fold<1><<<grid, block, 0, h->stream>>>(G, h->B, h->E[h->ecur], h->R);
-  else                k_fold<2><<<grid, block, 0, h->stream>>>(G, h->B, h->E[h->ecur], h->R);
+  if (!st) st = h->stream;
+  const dim3 grid(h->B.bx, h->B.by, mode == 3 ? std::min(2, h->B.bz) : h->B.bz), block(h->B.tx, h->B.ty);
+  if (mode == 0)      k_fold<0><<<grid, block, 0, st>>>(G, h->B, h->E[h->ecur], h->R);
+  else if (mode == 1) k_fold<1><<<grid, block, 0, st>>>(G, h->B, h->E[h->ecur], h->R);
+  else if (mode == 2) k_fold<2><<<grid, block, 0, st>>>(G, h->B, h->E[h->ecur], h->R);
+  else if (mode == 3) k_fold<3><<<grid, block, 0, st>>>(G, h->B, h->E[h->ecur], h->R);
+  else                k_fold<4><<<grid, block, 0, st>>>(G, h->B, h->E[h->ecur], h->R);
   ++h->launches;
   CU(cudaGetLastError());
   return 0;
@@ -324,27 +334,29 @@ int ensure_full_R(bflbm_lattice* h) {
   return 0;
 }
 
+// rows: 0 = every brick row, 1 = the first and the last row (two z-blocks), 2 = rows 1 .. bz-2
 template <bool NOISE, bool R1, bool FU>
-int launch_fused_v(bflbm_lattice* h) {
+int launch_fused_v(bflbm_lattice* h, int rows, cudaStream_t st) {
   const BrickGrid& B = h->B;
-  const dim3 grid(B.bx, B.by, B.bz), block(B.tx, B.ty);
+  const dim3 grid(B.bx, B.by, rows == 0 ? B.bz : (rows == 1 ? 2 : B.bz - 2)), block(B.tx, B.ty);
+  const int bz0 = rows == 2 ? 1 : 0, two_ends = rows == 1;
   const double2* Ein = (h->e_valid && h->fold_in_staging) ? h->E[h->ecur] : nullptr;
   double2* Eout = h->E[1 - h->ecur];
   const PopBases XB = make_pop_bases(h->G, h->X[h->cur], h->X[1 - h->cur]);
   if (B.tx * B.ty == 128)
-    k_step_fused<NOISE, R1, FU, 128><<<grid, block, fused_smem_bytes(B, R1), h->stream>>>(h->G, B, h->dp, h->step, XB, h->R, Ein, Eout);
+    k_step_fused<NOISE, R1, FU, 128><<<grid, block, fused_smem_bytes(B, R1), st>>>(h->G, B, h->dp, h->step, XB, h->R, Ein, Eout, bz0, two_ends);
   else
-    k_step_fused<NOISE, R1, FU, 256><<<grid, block, fused_smem_bytes(B, R1), h->stream>>>(h->G, B, h->dp, h->step, XB, h->R, Ein, Eout);
+    k_step_fused<NOISE, R1, FU, 256><<<grid, block, fused_smem_bytes(B, R1), st>>>(h->G, B, h->dp, h->step, XB, h->R, Ein, Eout, bz0, two_ends);
   ++h->launches;
   CU(cudaGetLastError());
   return 0;
 }
 template <bool NOISE>
-int launch_fused(bflbm_lattice* h) {
+int launch_fused(bflbm_lattice* h, int rows, cudaStream_t st) {
   const bool rate1 = h->rate1_fast_path && h->dp.rate_f == 1. && h->dp.rate_g == 1.;
   const bool full = h->G.nx % h->B.tx == 0 && h->G.ny % h->B.ty == 0;
-  if (rate1) return full ? launch_fused_v<NOISE, true, true>(h) : launch_fused_v<NOISE, true, false>(h);
-  return full ? launch_fused_v<NOISE, false, true>(h) : launch_fused_v<NOISE, false, false>(h);
+  if (rate1) return full ? launch_fused_v<NOISE, true, true>(h, rows, st) : launch_fused_v<NOISE, true, false>(h, rows, st);
+  return full ? launch_fused_v<NOISE, false, true>(h, rows, st) : launch_fused_v<NOISE, false, false>(h, rows, st);
 }
 
 // collide+stream of the slab and local density partials; leaves the outgoing messages packed
@@ -364,13 +376,34 @@ int step_local(bflbm_lattice* h) {
     mark(h, 1);
     return 0;
   }
-  int rc = noise ? launch_fused<true>(h) : launch_fused<false>(h);
+  // the default kernel folds the brick-interior planes itself while staging (next step): only the brick faces here
+  const bool partial = h->algo == 0 && h->fold_in_staging && fold_in_staging_ok(h->G, h->B);
+  int rc;
+  if (!h->whole_box && h->overlap && !h->profiling && partial && h->B.bz >= 3) {
+    // overlapped slab step.  stream: [first+last brick row] -> [fold of the 4 slab-face planes] -> [pack] -> caller's
+    // exchange -> (step_end) unpack.  aux: [interior rows] -> [fold of the other brick faces], concurrent with the exchange.
+    CU(cudaEventRecord(h->ev_prev, h->stream));          // everything queued so far (previous step, uploads, observers)
+    CU(cudaStreamWaitEvent(h->aux, h->ev_prev, 0));
+    if ((rc = noise ? launch_fused<true>(h, 1, h->stream) : launch_fused<false>(h, 1, h->stream))) return rc;
+    CU(cudaEventRecord(h->ev_ends, h->stream));
+    if ((rc = noise ? launch_fused<true>(h, 2, h->aux) : launch_fused<false>(h, 2, h->aux))) return rc;
+    h->cur ^= 1;
+    h->ecur ^= 1;
+    h->e_valid = true;
+    h->r_stale = true;
+    if ((rc = fold_local(h, 3))) return rc;
+    if ((rc = pack_halo(h))) return rc;
+    CU(cudaStreamWaitEvent(h->aux, h->ev_ends, 0));      // the brick faces next to the end rows need their extended boxes
+    if ((rc = fold_local(h, 4, h->aux))) return rc;
+    CU(cudaEventRecord(h->ev_interior, h->aux));
+    h->interior_pending = true;
+    return 0;
+  }
+  rc = noise ? launch_fused<true>(h, 0, h->stream) : launch_fused<false>(h, 0, h->stream);
   if (rc) return rc;
   h->cur ^= 1;
   h->ecur ^= 1;
   mark(h, 1);
-  // the default kernel folds the brick-interior planes itself while staging (next step): only the brick faces here
-  const bool partial = h->algo == 0 && h->fold_in_staging && fold_in_staging_ok(h->G, h->B);
   h->e_valid = partial;
   h->r_stale = partial;
   if ((rc = fold_local(h, partial ? 1 : 0))) return rc;
@@ -434,6 +467,15 @@ int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, 
   h->B = make_brick_grid(G, 0, h->cta_threads, 32);
   TRY(dev_alloc(h, &h->E[0], brick_doubles2(h->B)));
   TRY(dev_alloc(h, &h->E[1], brick_doubles2(h->B)));
+  if (!whole) {
+    const char* ov = getenv("BFLBM_OVERLAP");
+    h->overlap = !(ov && ov[0] == '0');
+    cudaError_t e = cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_prev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_ends, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_interior, cudaEventDisableTiming);
+    if (e != cudaSuccess) { bflbm_destroy(h); return fail(BFLBM_ERR_CUDA, "aux stream / events: %s", cudaGetErrorString(e)); }
+  }
   {
     const char* fs = getenv("BFLBM_FOLD_IN_STAGING");
     h->fold_in_staging = !(fs && fs[0] == '0');
@@ -501,37 +543,34 @@ int observe(bflbm_lattice* h, int ncomp, double* out, bool out_is_device, bool c
       CU(cudaMemcpy2DAsync(out + (size_t)zlo * G.plane, (size_t)G.nzl * G.plane * sizeof(double), h->stage,
                            (size_t)zc * G.plane * sizeof(double), (size_t)zc * G.plane * sizeof(double), ncomp, kind, h->stream));
     }
-    CU(cudaStreamSynchronize(h->stream));  // the stage is reused by the next chunk
+    // the stage is reused by the next chunk: stream order (kernel after copy) protects it, no host sync per chunk
   }
+  CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
 int upload_populations(bflbm_lattice* h, const double* f, const double* g, bool ghosted) {
   const Geom& G = h->G;
   int rc;
-  const int cp = chunk_planes(h, 2 * Q, 2);
-  if ((rc = ensure_stage(h, (size_t)(2 * Q) * (cp + 2) * G.plane))) return rc;
+  // host planes are the sources: [0, nzl) of a whole box, [-1, nzl] of a slab (ghosted arrays, host plane index + 1)
+  const int zfirst = ghosted ? -1 : 0, nsrc = ghosted ? G.nzl + 2 : G.nzl;
+  const size_t budget = (size_t)128 << 20;  // doubles (1 GiB): a few large copies per component instead of one per plane
+  int cp = (int)std::max<size_t>(1, std::min<size_t>((size_t)nsrc, budget / ((size_t)(2 * Q) * (size_t)G.plane)));
+  if ((rc = ensure_stage(h, (size_t)(2 * Q) * cp * G.plane))) return rc;
   const double* src[2] = {f, g};
-  const size_t hplanes = ghosted ? G.nzl + 2 : G.nzl;  // planes per component in the host arrays
-  for (int zlo = 0; zlo < G.nzl; zlo += cp) {
-    const int zc = std::min(cp, G.nzl - zlo), np = zc + 2;
-    for (int s = 0; s < 2; ++s) {
-      double* dst = h->stage + (size_t)s * Q * np * G.plane;
-      const size_t dpitch = (size_t)np * G.plane * sizeof(double), spitch = hplanes * G.plane * sizeof(double);
-      if (ghosted) {  // host planes zlo .. zlo+zc+1 are lattice planes zlo-1 .. zlo+zc
-        CU(cudaMemcpy2DAsync(dst, dpitch, src[s] + (size_t)zlo * G.plane, spitch, (size_t)np * G.plane * sizeof(double), Q, cudaMemcpyHostToDevice, h->stream));
-      } else {
-        CU(cudaMemcpy2DAsync(dst + G.plane, dpitch, src[s] + (size_t)zlo * G.plane, spitch, (size_t)zc * G.plane * sizeof(double), Q, cudaMemcpyHostToDevice, h->stream));
-        const int zm = (zlo - 1 + G.nzl) % G.nzl, zp = (zlo + zc) % G.nzl;  // periodic images (whole box)
-        CU(cudaMemcpy2DAsync(dst, dpitch, src[s] + (size_t)zm * G.plane, spitch, (size_t)G.plane * sizeof(double), Q, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemcpy2DAsync(dst + (size_t)(zc + 1) * G.plane, dpitch, src[s] + (size_t)zp * G.plane, spitch, (size_t)G.plane * sizeof(double), Q, cudaMemcpyHostToDevice, h->stream));
-      }
-    }
-    k_scatter_populations<<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, zlo, np, h->stage, h->X[h->cur]);
+  const size_t spitch = (size_t)nsrc * G.plane * sizeof(double);
+  for (int z = 0; z < nsrc; z += cp) {
+    const int zc = std::min(cp, nsrc - z);
+    const size_t dpitch = (size_t)zc * G.plane * sizeof(double);
+    for (int s = 0; s < 2; ++s)
+      CU(cudaMemcpy2DAsync(h->stage + (size_t)s * Q * zc * G.plane, dpitch, src[s] + (size_t)z * G.plane, spitch, dpitch, Q,
+                           cudaMemcpyHostToDevice, h->stream));
+    // stream order protects the stage: the next chunk's copies start after this kernel has read it (no host sync)
+    k_scatter_populations<<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, zfirst + z, ghosted ? 0 : 1, h->stage, h->X[h->cur]);
     ++h->launches;
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(h->stream));
   }
+  CU(cudaStreamSynchronize(h->stream));  // the caller's host buffers are free again
   return 0;
 }
 
@@ -557,6 +596,10 @@ int bflbm_destroy(bflbm_lattice* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
+  if (h->ev_prev) cudaEventDestroy(h->ev_prev);
+  if (h->ev_ends) cudaEventDestroy(h->ev_ends);
+  if (h->ev_interior) cudaEventDestroy(h->ev_interior);
   cudaFree(h->X[0]); cudaFree(h->X[1]); cudaFree(h->R); cudaFree(h->E[0]); cudaFree(h->E[1]);
   for (int s = 0; s < 2; ++s) { cudaFree(h->send[s]); cudaFree(h->recv[s]); }
   cudaFree(h->stage); cudaFree(h->diag_partial); cudaFree(h->diag_count);
@@ -708,6 +751,10 @@ int bflbm_step_end(bflbm_lattice* h) {
   CHECK_H(h);
   int rc = set_device(h);
   if (rc) return rc;
+  if (h->interior_pending) {  // join the interior rows before anything else touches the lattice
+    CU(cudaStreamWaitEvent(h->stream, h->ev_interior, 0));
+    h->interior_pending = false;
+  }
   double* const self[2] = {h->send[1], h->send[0]};
   if ((rc = unpack_halo(h, h->whole_box ? self : h->recv))) return rc;
   mark(h, 4);

@@ -156,7 +156,10 @@ template <bool NOISE, bool RATE1, bool FULL, int NT>
 __global__ void __launch_bounds__(NT, 512 / NT)
 k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B, const __grid_constant__ DevParams P, long long step,
              const __grid_constant__ PopBases XB, const double2* __restrict__ R, const double2* __restrict__ Ein,
-             double2* __restrict__ E) {
+             double2* __restrict__ E, int bz0, int two_ends) {
+  // brick row of this CTA: rows bz0 .. bz0+gridDim.z-1, or (two_ends) the first and the last row of the slab -- the
+  // rows whose results the halo message needs, launched first so that the exchange overlaps the interior rows
+  const int bZ = two_ends ? (blockIdx.z == 0 ? 0 : B.bz - 1) : bz0 + (int)blockIdx.z;
   extern __shared__ double2 smem[];
   double2* Rs = smem;             // [4][ey][ex] ring of (rho,phi) planes zl-1, zl, zl+1 and the one in flight (zl+2)
   double2* A = smem + 4 * B.pl;   // [3][ey][ex] rolling accumulators of next-step (rho,phi)
@@ -165,11 +168,11 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
   double* Sg = reinterpret_cast<double*>(Fix + FIX_SLOTS);  // [15][NT] parked moments 4..18 of species g (!RATE1)
   __shared__ int nfix;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * B.tx + tx;
-  const int x0 = blockIdx.x * B.tx, y0 = blockIdx.y * B.ty, zb = blockIdx.z * B.lz;
+  const int x0 = blockIdx.x * B.tx, y0 = blockIdx.y * B.ty, zb = bZ * B.lz;
   const int x = x0 + tx, y = y0 + ty;
   const bool active = FULL || (x < G.nx && y < G.ny);
   const int vz = min(B.lz, G.nzl - zb);
-  double2* Eb = E + (((long long)blockIdx.z * B.by + blockIdx.y) * B.bx + blockIdx.x) * B.brick;
+  double2* Eb = E + (((long long)bZ * B.by + blockIdx.y) * B.bx + blockIdx.x) * B.brick;
 
   // Staging of one (rho,phi) plane zl (-1..nzl) of the tile + ring into ring slot s, two entries per thread.
   //  - planes on a brick face in z (first / last plane of a brick, slab ghost planes) come from R, where k_fold
@@ -217,7 +220,7 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
       Tab[idx] = t;
     }
   }
-  const double2* Ein_row = Ein + (long long)blockIdx.z * B.by * B.bx * B.brick;                 // this brick row of Ein
+  const double2* Ein_row = Ein + (long long)bZ * B.by * B.bx * B.brick;                         // this brick row of Ein
   const double2* Ein_own = Ein_row + ((long long)blockIdx.y * B.bx + blockIdx.x) * B.brick;    // this brick
   auto from_R = [&](int zl) { const int l = zl - zb; return Ein == nullptr || l <= 0 || l >= vz - 1; };  // CTA-uniform
   auto stage_plane = [&](int zl, int s) {
@@ -449,9 +452,12 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
 // no integer division (the first, cell-per-thread version spent ~250 instructions per cell and ran at 2.6 TB/s).
 // MODE 0: every plane.  MODE 1: only what the step kernel does not fold itself -- the first and last plane of every
 // brick and the two slab-face outputs (zl = -1, nzl).  MODE 2: the complement of MODE 1 (on demand, for the observers).
+// MODE 3 + MODE 4 = MODE 1 split for the overlapped slab step: 3 = the four planes at the slab faces (zl = -1, 0,
+// nzl-1, nzl: all the halo message needs, computable from the first and last brick row alone; launched with two
+// z-blocks), 4 = the remaining brick-face planes.
 template <int MODE>
 __global__ void __launch_bounds__(256, 4) k_fold(Geom G, BrickGrid B, const double2* __restrict__ E, double2* __restrict__ R) {
-  const int bX = blockIdx.x, bY = blockIdx.y, bZ = blockIdx.z;
+  const int bX = blockIdx.x, bY = blockIdx.y, bZ = MODE == 3 ? (blockIdx.z == 0 ? 0 : B.bz - 1) : (int)blockIdx.z;
   const int lx = threadIdx.x, ly = threadIdx.y;
   const int x = bX * B.tx + lx, y = bY * B.ty + ly;
   if (x >= G.nx || y >= G.ny) return;
@@ -477,9 +483,10 @@ __global__ void __launch_bounds__(256, 4) k_fold(Geom G, BrickGrid B, const doub
   };
   const int zb = bZ * B.lz, vz = min(B.lz, G.nzl - zb);
   double2* Rc = R + (long long)y * G.nx + x;
-  if (MODE != 2) {
-    if (bZ == 0) Rc[0] = group(0, 0);  // zl = -1 : what this slab gives to the lower neighbour's boundary plane
-    if (bZ == B.bz - 1) Rc[(long long)(G.nzl + 1) * G.plane] = group(bZ, vz + 1);  // zl = nzl
+  if (MODE != 2 && MODE != 4) {
+    // with one brick row, MODE 3 runs a single z-block that owns both faces
+    if (bZ == 0 && (MODE != 3 || blockIdx.z == 0)) Rc[0] = group(0, 0);  // zl = -1 : my share of the lower neighbour's boundary plane
+    if (bZ == B.bz - 1 && (MODE != 3 || blockIdx.z == gridDim.z - 1)) Rc[(long long)(G.nzl + 1) * G.plane] = group(bZ, vz + 1);  // zl = nzl
   }
   auto plane = [&](int l) {
     double2 tot = group(bZ, l + 1);
@@ -498,6 +505,12 @@ __global__ void __launch_bounds__(256, 4) k_fold(Geom G, BrickGrid B, const doub
   if (MODE == 1) {
     plane(0);
     if (vz > 1) plane(vz - 1);
+  } else if (MODE == 3) {  // slab faces: plane 0 of the first row, the last plane of the last row
+    if (bZ == 0 && blockIdx.z == 0) plane(0);
+    if (bZ == B.bz - 1 && blockIdx.z == gridDim.z - 1 && !(bZ == 0 && vz == 1)) plane(vz - 1);
+  } else if (MODE == 4) {  // brick faces that are not slab faces
+    if (bZ > 0 && !(bZ == B.bz - 1 && vz == 1)) plane(0);
+    if (bZ < B.bz - 1 && vz > 1) plane(vz - 1);
   } else {
     const int lo = MODE == 2 ? 1 : 0, hi = MODE == 2 ? vz - 1 : vz;
 #pragma unroll 4

@@ -186,21 +186,28 @@ __global__ void __launch_bounds__(256) k_init(Geom G, InitSpec S, double* __rest
   }
 }
 
-// restart: staging holds post-stream populations f_i(x) for planes zl = zlo-1 .. zhi (one ghost plane on
-// each side of the chunk), component-major [38][np][ny][nx]; writes X_i(x) = f_i(x + c_i) for zl in [zlo, zhi).
-__global__ void __launch_bounds__(256) k_scatter_populations(Geom G, int zlo, int np, const double* __restrict__ stage,
+// Restart upload (LBM_init, LBM_binary.H:631-661): the host holds post-stream populations f_i(x); the lattice stores
+// them pre-stream, X_i(x - c_i) = f_i(x).  PUSH formulation: the chunk of host planes [zs, zs + gridDim.z) that has
+// just landed in `stage` (component-major, exactly those planes, no ghost planes) is written to its targets; every
+// lattice entry has exactly one source, so chunks are independent and nothing is uploaded twice.
+// wrap_z: whole box (targets wrap periodically); otherwise targets outside the slab belong to the neighbour and are
+// dropped (the host array of a slab carries the two ghost planes zs = -1 and nzl as sources for that reason).
+__global__ void __launch_bounds__(256) k_scatter_populations(Geom G, int zs0, int wrap_z, const double* __restrict__ stage,
                                                               double* __restrict__ X) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zl = zlo + (int)blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zs = zs0 + (int)blockIdx.z;
   if (x >= G.nx || y >= G.ny) return;
-  const CellIdx I = cell_idx(G, x, y, zl);
-  const long long c = I.zpl[1] + I.yrow[1] + x;
-  const long long scomp = (long long)np * G.plane;
+  const int xs[3] = {x == 0 ? G.nx - 1 : x - 1, x, x == G.nx - 1 ? 0 : x + 1};
+  const long long yr[3] = {(long long)(y == 0 ? G.ny - 1 : y - 1) * G.nx, (long long)y * G.nx, (long long)(y == G.ny - 1 ? 0 : y + 1) * G.nx};
+  const long long scomp = (long long)gridDim.z * G.plane;
+  const long long s = (long long)blockIdx.z * G.plane + yr[1] + x;
 #pragma unroll
   for (int i = 0; i < Q; ++i) {
-    // source plane index inside the stage: (zl + cz) - (zlo - 1)
-    const long long s = (long long)(zl + cz(i) - zlo + 1) * G.plane + I.yrow[1 + cy(i)] + I.xs[1 + cx(i)];
-    X[(long long)i * G.comp + c] = stage[(long long)i * scomp + s];
-    X[(long long)(Q + i) * G.comp + c] = stage[(long long)(Q + i) * scomp + s];
+    int zt = zs - cz(i);
+    if (wrap_z) zt = zt < 0 ? zt + G.nzl : (zt >= G.nzl ? zt - G.nzl : zt);
+    if (zt < 0 || zt >= G.nzl) continue;
+    const long long t = (long long)(zt + 1) * G.plane + yr[1 - cy(i)] + xs[1 - cx(i)];
+    X[(long long)i * G.comp + t] = stage[(long long)i * scomp + s];
+    X[(long long)(Q + i) * G.comp + t] = stage[(long long)(Q + i) * scomp + s];
   }
 }
 

@@ -288,17 +288,20 @@ def test_center_of_mass_and_mass(bflbm, oracle_mod):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # slab decomposition (the multi-GPU path), emulated on one GPU: P slabs, device-to-device copies instead of NCCL
+@pytest.mark.parametrize("lz", [2, 4])
 @pytest.mark.parametrize("nslabs", [2, 3, 4])
 @pytest.mark.parametrize("kbt", [0.0, 1e-5])
-def test_slabs_bitwise_equal_to_whole_box(bflbm, nslabs, kbt):
-    """results must not depend on the number of slabs.  Same brick height => bit-identical."""
+def test_slabs_bitwise_equal_to_whole_box(bflbm, nslabs, kbt, lz):
+    """results must not depend on the number of slabs.  Same brick height => bit-identical.
+    Slabs have >= 3 brick rows, so the overlapped step (end rows + exchange on one stream, interior rows on a second)
+    is the path under test; lz = 4 adds planes that the step kernel folds itself from the extended boxes."""
     from bflbm_b200.distributed import EmulatedSlabs
-    shape = (20, 12, 24)
+    shape = (20, 12, 48)
     prm = bflbm.Params(kBT=kbt, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, tau_f=0.7, tau_g=0.55, seed=99)
     with bflbm.Lattice(*shape, params=prm) as whole:
-        whole.set_tiling(2)
+        whole.set_tiling(lz)
         whole.init_droplet(0.3)
-        S = EmulatedSlabs(*shape, nslabs, params=prm, brick_lz=2)
+        S = EmulatedSlabs(*shape, nslabs, params=prm, brick_lz=lz)
         try:
             S.init_droplet(0.3)
             for _ in range(3):
