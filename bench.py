@@ -181,6 +181,8 @@ def run_b200(a):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the b200 arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nzl = a.nz
     nz_global = nzl * world

@@ -206,10 +206,14 @@ class SlabLattice:
         f, g = lat.populations()  # untimed: makes the host checkpoint of this slab
         # ghost planes of the host checkpoint come from the ring neighbours (host-side exchange through the GPUs' path
         # would hide the cost, so it is done here once, untimed, like reading a checkpoint file that already has them)
-        fg = np.empty((2, NVEL, self.nzl + 2, lat.ny, lat.nx))
+        try:  # pinned host checkpoint, like the single-GPU leg
+            fg = torch.empty((2, NVEL, self.nzl + 2, lat.ny, lat.nx), dtype=torch.float64, pin_memory=True).numpy()
+        except Exception:
+            fg = np.empty((2, NVEL, self.nzl + 2, lat.ny, lat.nx))
         fg[0, :, 1:-1], fg[1, :, 1:-1] = f, g
         lo_send = torch.from_numpy(np.ascontiguousarray(np.stack([f[:, 0], g[:, 0]]))).to(self.device)
         hi_send = torch.from_numpy(np.ascontiguousarray(np.stack([f[:, -1], g[:, -1]]))).to(self.device)
+        del f, g
         lo_recv, hi_recv = torch.empty_like(lo_send), torch.empty_like(hi_send)
         exchange_ring(lo_send, hi_send, lo_recv, hi_recv, self.rank, self.world, self.group)
         fg[:, :, 0] = lo_recv.cpu().numpy()

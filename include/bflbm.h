@@ -79,8 +79,8 @@ int bflbm_get_params(const bflbm_lattice* h, bflbm_params* p);
 
 /* Use the caller's CUDA stream (a cudaStream_t) for all subsequent work; NULL = the library's own. */
 int bflbm_set_stream(bflbm_lattice* h, void* cuda_stream);
-/* 0 = one-pass fused step, one thread per cell (default); 1 = two-pass step (density kernel + collide/stream
- * kernel, whole-box lattices only); 2 = one-pass fused step, species-split (two threads per cell). */
+/* 0 = one-pass fused step (default); 1 = two-pass step (density kernel + collide/stream kernel, whole-box lattices
+ * only; kept as an independent cross-check of the fused path). */
 int bflbm_set_algorithm(bflbm_lattice* h, int algo);
 /* Height (planes) of the CTA bricks of the fused step; 0 = automatic.  Results are bit-identical for any
  * number of slabs as long as every slab uses the same brick height and it divides nz_local. */
@@ -134,9 +134,11 @@ int bflbm_check_nan(bflbm_lattice* h, long long* count);
 /* ---- slab halo exchange (replaces the 7 FillBoundary calls per step, LBM_binary.H:130-131,312,353,
  * 553-555, by ONE message per neighbour per step) -------------------------------------------------
  * side 0 = towards lower z, side 1 = towards higher z.  A message is bflbm_halo_doubles() float64s.
- *   bflbm_step_begin : collide+stream on the slab, then pack both outgoing messages
- *   (caller moves send(side) of rank r to recv(1-side) of the neighbour: NCCL send/recv or P2P)
- *   bflbm_step_end   : unpack both messages, finish the density field; the step counter advances.
+ *   bflbm_step_begin : collide+stream of the first and last brick row, then pack both outgoing messages, all on the
+ *                      lattice's stream; the interior rows are launched on a second, internal stream and run while
+ *   (the caller moves send(side) of rank r to recv(1-side) of the neighbour on the lattice's stream: NCCL send/recv or P2P)
+ *   bflbm_step_end   : join the interior rows, unpack both messages, finish the density field; the step counter
+ *                      advances.  No other call on the lattice is allowed between _begin and _end.
  * bflbm_halo_refresh_begin/_end do the same exchange without stepping (after an init). */
 size_t bflbm_halo_doubles(const bflbm_lattice* h);
 void* bflbm_halo_send_buffer(bflbm_lattice* h, int side); /* device pointers, valid for the lattice's life */
