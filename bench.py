@@ -45,7 +45,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=512)
     ap.add_argument("--ny", type=int, default=512)
-    ap.add_argument("--nz", type=int, default=512, help="planes PER GPU (weak scaling)")
+    ap.add_argument("--nz", type=int, default=512, help="planes PER GPU (weak scaling) / of the whole box (strong scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, BASELINE configs[4]): nz planes per GPU; strong (configs[3]): nz planes in total, split over the GPUs")
     ap.add_argument("--algo", default="fused", choices=["fused", "twopass"])
     ap.add_argument("--kbt", type=float, default=PARAMS["kBT"])
     ap.add_argument("--brick-lz", type=int, default=0)
@@ -184,8 +186,13 @@ def run_b200(a):
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nzl = a.nz
-    nz_global = nzl * world
+    if a.scaling == "strong":
+        if a.nz % world:
+            raise SystemExit("bench.py --scaling strong: --nz must be divisible by the number of GPUs")
+        nzl, nz_global = a.nz // world, a.nz
+    else:
+        nzl = a.nz
+        nz_global = nzl * world
     prm = b.Params(**{**PARAMS, "kBT": a.kbt})
     stream = torch.cuda.Stream()  # a real (non-default) stream: the library launches on it and the events are recorded on it
     torch.cuda.set_stream(stream)
@@ -275,10 +282,11 @@ def run_b200(a):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"weak-scaling {a.nx}x{a.ny}x{nzl} cells per GPU ({a.nx}x{a.ny}x{nz_global} total), fluctuating binary "
-                                   f"D3Q19 mixture rho=phi=1, kBT={a.kbt:g}, alpha0={PARAMS['alpha0']}, tau_f=tau_g=1/2 (BASELINE.json configs[4])",
+            "config": {"workload": f"{a.scaling}-scaling {a.nx}x{a.ny}x{nzl} cells per GPU ({a.nx}x{a.ny}x{nz_global} total), fluctuating binary "
+                                   f"D3Q19 mixture rho=phi=1, kBT={a.kbt:g}, alpha0={PARAMS['alpha0']}, tau_f=tau_g=1/2 "
+                                   f"(BASELINE.json configs[{4 if a.scaling == 'weak' else 3}])",
                        "cells_per_gpu": cells_local, "algorithm": a.algo, "parallelism": f"z-slabs x{world}",
                        "l2": "working set (two lattices, %.1f GB per GPU) far exceeds the 126 MB L2; no flush needed" % (lat.device_bytes / 1e9),
                        "nonfinite_after_run": nan_count},

@@ -465,6 +465,8 @@ int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, 
     h->cta_threads = (nt && atoi(nt) == 128) ? 128 : 256;
   }
   h->B = make_brick_grid(G, 0, h->cta_threads, 32);
+  // a slab wants at least 3 brick rows so that the halo exchange can overlap the interior rows (thin strong-scaling slabs)
+  while (!whole && h->B.bz < 3 && h->B.lz >= 16) h->B = make_brick_grid(G, h->B.lz / 2, h->cta_threads, 32);
   TRY(dev_alloc(h, &h->E[0], brick_doubles2(h->B)));
   TRY(dev_alloc(h, &h->E[1], brick_doubles2(h->B)));
   if (!whole) {
