@@ -160,6 +160,8 @@ void derive(bflbm_lattice* h) {
   const double A = 2. * (lam - 0.5 * lam * lam);
   d.amp_j = A * p.kBT;
   d.amp_s = A * p.kBT / (1. / 3.);
+  d.sqrt_amp_j = sqrt(d.amp_j);
+  d.sqrt_amp_s = sqrt(d.amp_s);
   d.keys = philox_key_schedule(p.seed);
 }
 

@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) k_observe(Geom G, DevParams P, long long 
     float n[36];
     cell_normals(nk, n);
 #pragma unroll
-    for (int d = 0; d < 33; ++d) out[o * 33 + d] = (double)n[d];
+    for (int d = 0; d < 33; ++d) out[o * 33 + d] = widen(n[d]);
     return;
   }
   double f[Q], g[Q];
@@ -273,14 +273,14 @@ __global__ void __launch_bounds__(256) k_observe(Geom G, DevParams P, long long 
     out[(long long)Q * oc + o] = 0.;
 #pragma unroll
     for (int a = 1; a <= 3; ++a) {
-      const double v = aj * (double)n[a - 1];
+      const double v = aj * widen(n[a - 1]);
       out[(long long)a * oc + o] = v;
       out[(long long)(Q + a) * oc + o] = -v;
     }
 #pragma unroll
     for (int a = 4; a < Q; ++a) {
-      out[(long long)a * oc + o] = (sqrt_bnorm(a) * sf) * (double)n[3 + 2 * (a - 4)];
-      out[(long long)(Q + a) * oc + o] = (sqrt_bnorm(a) * sg) * (double)n[4 + 2 * (a - 4)];
+      out[(long long)a * oc + o] = (sqrt_bnorm(a) * sf) * widen(n[3 + 2 * (a - 4)]);
+      out[(long long)(Q + a) * oc + o] = (sqrt_bnorm(a) * sg) * widen(n[4 + 2 * (a - 4)]);
     }
     return;
   }
@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(256) k_observe(Geom G, DevParams P, long long 
     const float n3[3] = {n[0], n[1], n[2]};
     const double jf[3] = {mf[1], mf[2], mf[3]}, jg[3] = {mg[1], mg[2], mg[3]};
     CellHydro H;
-    cell_hydro<NOISE>(P, rho, phi, jf, jg, grho, gphi, n3, H);
+    double sq_rho, sq_phi;
+    cell_hydro<NOISE>(P, rho, phi, jf, jg, grho, gphi, n3, H, sq_rho, sq_phi);
     out[0 * oc + o] = rho;
     out[1 * oc + o] = phi;
     out[5 * oc + o] = rho + phi;

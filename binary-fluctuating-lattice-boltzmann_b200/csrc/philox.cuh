@@ -63,6 +63,16 @@ __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.
 __device__ __forceinline__ float fast_sin(float x) { float r; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_cos(float x) { float r; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
+// float -> double by integer re-packing (exponent re-bias, mantissa shift): exact for every normal float; the generator's
+// outputs are flush-to-zero, so the only other input is 0, which comes out as 2^-127 (5.9e-39 -- noise of that size is
+// nothing).  Why not cvt.f64.f32: the 33 conversions per cell go through the low-rate conversion unit (SASS F2F) and
+// cost 1.25 ms of a 17 ms step at 512^3 (measured by replacing them, profiles/README.md); these are 4 ALU operations.
+__device__ __forceinline__ double widen(float f) {
+  const unsigned u = __float_as_uint(f);
+  const unsigned hi = (((u & 0x7fffffffu) >> 3) + 0x38000000u) | (u & 0x80000000u);
+  return __hiloint2double((int)hi, (int)(u << 29));
+}
+
 // one Philox word -> two independent standard normals
 __device__ __forceinline__ void box_muller(uint32_t w, float& n0, float& n1) {
   // U in (0,1): (w>>10 + 0.5) / 2^22 ; theta = 2 pi (w & 1023 + 0.5) / 1024 ; both conversions are exact in fp32

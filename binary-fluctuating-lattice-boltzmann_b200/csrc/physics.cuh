@@ -21,6 +21,7 @@ struct DevParams {
   double acc_coef;        // -cs2 * alpha0                     LBM_binary.H:254-255
   double amp_j;           // A kBT,      A = 2(l - l^2/2), l = 1/(tau_f + 1/2)   LBM_binary.H:79-82,117
   double amp_s;           // A kBT / cs2                                          LBM_binary.H:125-126
+  double sqrt_amp_j, sqrt_amp_s;  // their square roots (the amplitudes are sqrt(amp) * sqrt|density|)
   PhiloxKeys keys;        // Philox round keys of the seed (LBM_binary.H:17)
 };
 
@@ -40,26 +41,45 @@ __device__ __forceinline__ void gradient19(const double (&n)[Q], double (&g)[3])
   g[2] = (1. / 6.) * (n[5] - n[6]) + (1. / 12.) * (((n[11] - n[12]) - (n[13] - n[14])) + ((n[15] - n[16]) - (n[17] - n[18])));
 }
 
-// n3: the first three standard normals of the cell (draws 0..2), ignored when !NOISE
+// 1/sqrt(x) for x > 0 to ~1 ulp: hardware seed (rsqrt.approx.f64 = MUFU.RSQ64H, ~2^-22) + two Newton steps.
+// No special-case code (the callers guard x = 0): 9 instructions instead of the ~15 + slow-path branch of sqrt() or 1/x.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+
+// n3: the first three standard normals of the cell (draws 0..2), ignored when !NOISE.
+// sq_rho / sq_phi return sqrt|rho|, sqrt|phi| (for the stress-mode noise amplitudes of collide_species).
+// The three reciprocals (1/rho, 1/phi, 1/(rho+phi)) and three square roots the formulas need all come from three
+// reciprocal square roots: 1/x = sign(x) r^2, sqrt|x| = |x| r with r = rsqrt|x|  (each ~2 ulp; the bar is 1e-12).
 template <bool NOISE>
 __device__ __forceinline__ void cell_hydro(const DevParams& P, double rho, double phi, const double (&jf)[3], const double (&jg)[3],
                                            const double (&grad_rho)[3], const double (&grad_phi)[3], const float (&n3)[3],
-                                           CellHydro& H) {
+                                           CellHydro& H, double& sq_rho, double& sq_phi) {
   H.rho = rho;
   H.phi = phi;
   const bool has_f = fabs(rho) > (double)FLT_EPSILON, has_g = fabs(phi) > (double)FLT_EPSILON;
-  const double inv_rho = has_f ? 1. / rho : 0., inv_phi = has_g ? 1. / phi : 0.;
   const double tot = rho + phi;
-  H.inv_tot = 1. / tot;  // unguarded, like the reference (LBM_binary.H:266-272, 286-288, 471)
+  const double ar = fabs(rho), ap = fabs(phi), at = fabs(tot);
+  const double rr = rsqrt_pos(ar), rp = rsqrt_pos(ap), rt = rsqrt_pos(at);
+  const double inv_rho = has_f ? copysign(rr * rr, rho) : 0., inv_phi = has_g ? copysign(rp * rp, phi) : 0.;
+  H.inv_tot = copysign(rt * rt, tot);  // unguarded, like the reference (LBM_binary.H:266-272, 286-288, 471): tot = 0 -> inf
+  sq_rho = ar > 0. ? ar * rr : 0.;
+  sq_phi = ap > 0. ? ap * rp : 0.;
   double amp = 0.;
-  if (NOISE) amp = sqrt(P.amp_j * fabs(rho * phi * H.inv_tot));
+  // sqrt(A kBT |rho phi / (rho + phi)|)  (LBM_binary.H:117) = sqrt(A kBT) sqrt|rho| sqrt|phi| / sqrt|rho + phi|
+  if (NOISE) amp = P.sqrt_amp_j * (sq_rho * sq_phi) * rt;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     H.ufb[k] = jf[k] * inv_rho;
     H.ugb[k] = jg[k] * inv_phi;
     H.af[k] = has_f ? P.acc_coef * grad_phi[k] : 0.;
     H.ag[k] = has_g ? P.acc_coef * grad_rho[k] : 0.;
-    H.xi[k] = NOISE ? amp * (double)n3[k] : 0.;
+    H.xi[k] = NOISE ? amp * widen(n3[k]) : 0.;
     H.nfv[k] = H.xi[k] * inv_rho;
     H.ngv[k] = -H.xi[k] * inv_phi;
     const double d = (H.ufb[k] - H.ugb[k]) + 0.5 * (H.af[k] - H.ag[k]);
@@ -103,6 +123,7 @@ __device__ __forceinline__ void relax_species(double rate, double pf, double D, 
 struct CollideCtx {
   CellHydro H;
   double vb[3];
+  double sq_rho, sq_phi;  // sqrt|rho|, sqrt|phi|
 };
 
 template <bool NOISE>
@@ -112,7 +133,7 @@ __device__ __forceinline__ void collide_prepare(const DevParams& P, const double
   if (NOISE) species_normals<0, 0, 4>(nk, n0);
   const float n3[3] = {n0[0], n0[1], n0[2]};
   const double jf[3] = {mf[1], mf[2], mf[3]}, jg[3] = {mg[1], mg[2], mg[3]};
-  cell_hydro<NOISE>(P, mf[0], mg[0], jf, jg, grad_rho, grad_phi, n3, C.H);
+  cell_hydro<NOISE>(P, mf[0], mg[0], jf, jg, grad_rho, grad_phi, n3, C.H, C.sq_rho, C.sq_phi);
 #pragma unroll
   for (int k = 0; k < 3; ++k) C.vb[k] = (C.H.rho * C.H.uf[k] + C.H.phi * C.H.ug[k]) * C.H.inv_tot;  // LBM_binary.H:471
 }
@@ -126,13 +147,13 @@ __device__ __forceinline__ void collide_species(const DevParams& P, const NoiseK
   if (NOISE) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) m[1 + k] += (SPECIES == 0 ? H.xi[k] : -H.xi[k]);
-    const double s = sqrt(P.amp_s * fabs(SPECIES == 0 ? H.rho : H.phi));
+    const double s = P.sqrt_amp_s * (SPECIES == 0 ? C.sq_rho : C.sq_phi);  // sqrt(A kBT/cs2 |density|), LBM_binary.H:125-126
     // modes 4..18 : normals F[3..17] (the pair F[2], F[3] is recomputed from block 0, already live) / G[0..14]
     constexpr int LO = SPECIES == 0 ? 2 : 0, HI = SPECIES == 0 ? 18 : 15;
     float nb[HI - LO + 1];
     species_normals<SPECIES, LO, HI>(nk, nb);
 #pragma unroll
-    for (int a = 4; a < Q; ++a) m[a] += (sqrt_bnorm(a) * s) * (double)nb[mode_index(SPECIES, a) - LO];
+    for (int a = 4; a < Q; ++a) m[a] += (sqrt_bnorm(a) * s) * widen(nb[mode_index(SPECIES, a) - LO]);
   }
 }
 
