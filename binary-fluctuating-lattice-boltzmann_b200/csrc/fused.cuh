@@ -311,11 +311,13 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
     const bool left = tx == 0;
     {
       double mf[Q], mg[Q];
+      float nbg[15];
       unsigned c = 0;  // byte offset of this cell inside a component
       CollideCtx C;
       NoiseKey nk;
       if (active) {
-        // gradients first (LBM_binary.H:134-150): only 6 doubles stay live across the population loads
+        // gradients first (LBM_binary.H:134-150): only 6 doubles stay live across the population loads (moving them into
+        // the load shadow as well was measured: +2.5 % without noise)
         double grho[3], gphi[3];
         {
           double nr[Q], np[Q];
@@ -344,23 +346,29 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
             off[i] = o;
           }
         }
+        float n3[3], nbf[15];
         {
-          double f[Q];
-          // species g first: its non-conserved moments wait in shared memory while species f is processed
+          double fg[Q], ff[Q];
+          // all 38 pulls are issued first; the random numbers of species f -- pure arithmetic on the cell's counter --
+          // are generated in their shadow, before the first loaded value is touched
 #pragma unroll
-          for (int i = 0; i < Q; ++i) f[i] = ld_off(XB.in[Q + i], off[i]);
-          moments(f, mg);
+          for (int i = 0; i < Q; ++i) fg[i] = ld_off(XB.in[Q + i], off[i]);
+#pragma unroll
+          for (int i = 0; i < Q; ++i) ff[i] = ld_off(XB.in[i], off[i]);
+          nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
+          momentum_normals<NOISE>(nk, n3);
+          mode_normals<NOISE, 0>(nk, nbf);
+          mode_normals<NOISE, 1>(nk, nbg);
+          // species g: its non-conserved moments wait in shared memory while species f is processed (general rates)
+          moments(fg, mg);
           if (!RATE1) {
 #pragma unroll
             for (int a = 4; a < Q; ++a) Sg[(a - 4) * NT + tid] = mg[a];
           }
-#pragma unroll
-          for (int i = 0; i < Q; ++i) f[i] = ld_off(XB.in[i], off[i]);
-          moments(f, mf);
+          moments(ff, mf);
         }
-        nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
-        collide_prepare<NOISE>(P, grho, gphi, nk, mf, mg, C);
-        collide_species<NOISE, 0, RATE1>(P, nk, C, mf);
+        collide_prepare<NOISE>(P, grho, gphi, n3, mf, mg, C);
+        collide_species<NOISE, 0, RATE1>(P, nbf, C, mf);
       } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) mf[i] = 0.;
@@ -380,7 +388,7 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
 #pragma unroll
           for (int a = 4; a < Q; ++a) mg[a] = Sg[(a - 4) * NT + tid];
         }
-        collide_species<NOISE, 1, RATE1>(P, nk, C, mg);
+        collide_species<NOISE, 1, RATE1>(P, nbg, C, mg);
       } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) mg[i] = 0.;

@@ -105,14 +105,18 @@ __global__ void __launch_bounds__(256) k_step_twopass(Geom G, DevParams P, long 
   density_gradients(R, I, grho, gphi);
   const NoiseKey nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
   CollideCtx C;
-  collide_prepare<NOISE>(P, grho, gphi, nk, mf, mg, C);
+  float n3[3], nb[15];
+  momentum_normals<NOISE>(nk, n3);
+  collide_prepare<NOISE>(P, grho, gphi, n3, mf, mg, C);
   const long long c = I.zpl[1] + I.yrow[1] + x;
   double f[Q];
-  collide_species<NOISE, 0>(P, nk, C, mf);
+  mode_normals<NOISE, 0>(nk, nb);
+  collide_species<NOISE, 0>(P, nb, C, mf);
   populations(mf, f);
 #pragma unroll
   for (int i = 0; i < Q; ++i) Xn[(long long)i * G.comp + c] = f[i];
-  collide_species<NOISE, 1>(P, nk, C, mg);
+  mode_normals<NOISE, 1>(nk, nb);
+  collide_species<NOISE, 1>(P, nb, C, mg);
   populations(mg, f);
 #pragma unroll
   for (int i = 0; i < Q; ++i) Xn[(long long)(Q + i) * G.comp + c] = f[i];

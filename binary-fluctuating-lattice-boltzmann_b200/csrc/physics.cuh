@@ -126,12 +126,12 @@ struct CollideCtx {
   double sq_rho, sq_phi;  // sqrt|rho|, sqrt|phi|
 };
 
+// The standard normals come from the caller (momentum_normals / mode_normals below): n3 = the three momentum-mode
+// draws, nb = the 15 draws of modes 4..18 of the species.  Generating them is pure arithmetic on the cell's counter,
+// so the step kernel does it in the shadow of its population loads, before the first loaded value is needed.
 template <bool NOISE>
 __device__ __forceinline__ void collide_prepare(const DevParams& P, const double (&grad_rho)[3], const double (&grad_phi)[3],
-                                                const NoiseKey& nk, const double (&mf)[Q], const double (&mg)[Q], CollideCtx& C) {
-  float n0[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  if (NOISE) species_normals<0, 0, 4>(nk, n0);
-  const float n3[3] = {n0[0], n0[1], n0[2]};
+                                                const float (&n3)[3], const double (&mf)[Q], const double (&mg)[Q], CollideCtx& C) {
   const double jf[3] = {mf[1], mf[2], mf[3]}, jg[3] = {mg[1], mg[2], mg[3]};
   cell_hydro<NOISE>(P, mf[0], mg[0], jf, jg, grad_rho, grad_phi, n3, C.H, C.sq_rho, C.sq_phi);
 #pragma unroll
@@ -140,7 +140,7 @@ __device__ __forceinline__ void collide_prepare(const DevParams& P, const double
 
 // SPECIES 0 = f (call first), 1 = g
 template <bool NOISE, int SPECIES, bool RATE1 = false>
-__device__ __forceinline__ void collide_species(const DevParams& P, const NoiseKey& nk, CollideCtx& C, double (&m)[Q]) {
+__device__ __forceinline__ void collide_species(const DevParams& P, const float (&nb)[15], CollideCtx& C, double (&m)[Q]) {
   const CellHydro& H = C.H;
   if (SPECIES == 0) relax_species<RATE1>(P.rate_f, P.force_pf, H.rho, C.vb, H.uf, H.af, m);
   else              relax_species<RATE1>(P.rate_g, P.force_pf, H.phi, C.vb, H.ug, H.ag, m);
@@ -148,12 +148,29 @@ __device__ __forceinline__ void collide_species(const DevParams& P, const NoiseK
 #pragma unroll
     for (int k = 0; k < 3; ++k) m[1 + k] += (SPECIES == 0 ? H.xi[k] : -H.xi[k]);
     const double s = P.sqrt_amp_s * (SPECIES == 0 ? C.sq_rho : C.sq_phi);  // sqrt(A kBT/cs2 |density|), LBM_binary.H:125-126
-    // modes 4..18 : normals F[3..17] (the pair F[2], F[3] is recomputed from block 0, already live) / G[0..14]
-    constexpr int LO = SPECIES == 0 ? 2 : 0, HI = SPECIES == 0 ? 18 : 15;
-    float nb[HI - LO + 1];
-    species_normals<SPECIES, LO, HI>(nk, nb);
 #pragma unroll
-    for (int a = 4; a < Q; ++a) m[a] += (sqrt_bnorm(a) * s) * widen(nb[mode_index(SPECIES, a) - LO]);
+    for (int a = 4; a < Q; ++a) m[a] += (sqrt_bnorm(a) * s) * widen(nb[a - 4]);
+  }
+}
+
+template <bool NOISE>
+__device__ __forceinline__ void momentum_normals(const NoiseKey& nk, float (&n3)[3]) {
+  float n0[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (NOISE) species_normals<0, 0, 4>(nk, n0);
+  n3[0] = n0[0]; n3[1] = n0[1]; n3[2] = n0[2];
+}
+template <bool NOISE, int SPECIES>
+__device__ __forceinline__ void mode_normals(const NoiseKey& nk, float (&nb)[15]) {
+  if (NOISE) {
+    // modes 4..18 : normals F[3..17] (the pair F[2], F[3] comes from block 0, shared with the momentum draws) / G[0..14]
+    constexpr int LO = SPECIES == 0 ? 2 : 0, HI = SPECIES == 0 ? 18 : 15;
+    float t[HI - LO + 1];
+    species_normals<SPECIES, LO, HI>(nk, t);
+#pragma unroll
+    for (int a = 4; a < Q; ++a) nb[a - 4] = t[mode_index(SPECIES, a) - LO];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 15; ++j) nb[j] = 0.f;
   }
 }
 
