@@ -32,6 +32,21 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+SF_LIB = os.path.join(HERE, "libbflbm_sf.so")
+
+
+def build_sf(force: bool = False) -> str:
+    """Compile csrc/sf.cu (on-GPU structure-factor accumulator, cuFFT) into libbflbm_sf.so on top of libbflbm.so."""
+    build()
+    src = os.path.join(CSRC, "sf.cu")
+    deps = [src, LIB, os.path.join(HERE, "..", "include", "bflbm_sf.h")]
+    if not force and os.path.exists(SF_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(SF_LIB) for d in deps):
+        return SF_LIB
+    cmd = [nvcc()] + NVCC_FLAGS + [src, "-o", SF_LIB, "-L" + HERE, "-lbflbm", "-lcufft", "-Xlinker", "-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return SF_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ into libbflbm.so next to this file (in-tree, so it travels with the repo)."""
     if not force and not needs_build():

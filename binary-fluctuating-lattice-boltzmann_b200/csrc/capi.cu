@@ -798,6 +798,15 @@ int bflbm_sync(bflbm_lattice* h) {
   return 0;
 }
 long long bflbm_step_count(const bflbm_lattice* h) { return h ? h->step : -1; }
+int bflbm_get_dims(const bflbm_lattice* h, int* nx, int* ny, int* nz_local, int* z0, int* nz_global) {
+  CHECK_H(h);
+  if (nx) *nx = h->G.nx;
+  if (ny) *ny = h->G.ny;
+  if (nz_local) *nz_local = h->G.nzl;
+  if (z0) *z0 = h->G.z0;
+  if (nz_global) *nz_global = h->G.nz_global;
+  return 0;
+}
 
 int bflbm_get_populations(bflbm_lattice* h, double* f, double* g) {
   CHECK_H(h);

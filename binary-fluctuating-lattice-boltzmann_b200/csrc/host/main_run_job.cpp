@@ -6,7 +6,9 @@
 //   bflbm_run_job <Parameters file> [key=value ...]      (trailing key=value pairs override the file)
 //
 // File names follow main_run_job.cpp:150-202 (plot_file_dir, lbm_data_shshan_alpha0_.._xi_.._size.., f_checkpoint..).
-// Out of scope: FHDeX StructFact, droplet radius fit.
+// Structure factors (FHDeX StructFact in the reference, main_run_job.cpp:299-310, 330, 342-349, 50-54): accumulated on the
+// GPU by libbflbm_sf.so (include/bflbm_sf.h) every out_SF_step steps inside the last plot_SF_window steps and written as
+// <plot_file_root>_SF<step> at the last step.  Out of scope: droplet radius fit.
 #include <chrono>
 #include <cstdarg>
 #include <cmath>
@@ -15,6 +17,7 @@
 #include <iostream>
 #include <sstream>
 
+#include "../../../include/bflbm_sf.h"
 #include "bflbm.hpp"
 #include "parameters.hpp"
 #include "plotfile.hpp"
@@ -100,6 +103,16 @@ int main(int argc, char** argv) {
     if (R.plot_int > 0 && R.step_continue == 0) write_output(0);
     std::printf("LB initialized with alpha0 = %g and T = %g\n", R.alpha0, R.kBT);
 
+    // ---- StructFact set-up, main_run_job.cpp:299-310 (pairs over hydrovs; only with noise and a window) -----------
+    const int plot_SF = noiseSwitch ? R.plot_SF_window : 0;  // main_run_job.cpp:102
+    const int SF_start = R.step_continue + R.nsteps - R.plot_SF_window;  // main_run_job.cpp:330
+    const std::vector<int> pairA = {0, 1, 0, 2, 3, 4, 6, 7, 8, 2, 9, 15, 16, 17, 15, 18, 19, 20, 21, 20, 20, 21};
+    const std::vector<int> pairB = {0, 1, 1, 2, 3, 4, 6, 7, 8, 6, 9, 15, 16, 17, 16, 18, 19, 20, 21, 21, 18, 18};
+    bflbm_sf* structFact = nullptr;
+    if (plot_SF > 0 && R.out_SF_step > 0 &&
+        bflbm_sf_create(L.handle(), (int)pairA.size(), pairA.data(), pairB.data(), nullptr, &structFact))
+      throw std::runtime_error("structure-factor accumulator: creation failed");
+
     // ---- time loop, main_run_job.cpp:329-387 ------------------------------------------------------------------
     const auto t_loop = std::chrono::steady_clock::now();
     const int last = R.step_continue + R.nsteps;
@@ -113,8 +126,11 @@ int main(int argc, char** argv) {
       upto(R.print_int);
       upto(R.plot_int);
       if (noiseSwitch) upto(R.out_noise_step);
+      if (structFact) upto(R.out_SF_step);
       LBM_timestep(L, next - step);
       step = next;
+      if (structFact && step >= SF_start && step % R.out_SF_step == 0 && bflbm_sf_accumulate(structFact))  // FortStructure(hydrovs, 0)
+        throw std::runtime_error("structure-factor accumulator: accumulate failed");
       if (R.print_int > 0 && step % R.print_int == 0) std::printf("LB step %d info:\n", step);
       if (noiseSwitch && R.out_noise_step > 0 && step % R.out_noise_step == 0) {  // WriteOutNoise, Debug.H:380-409
         auto nz2 = L.noise();
@@ -131,8 +147,20 @@ int main(int argc, char** argv) {
         }
         if (step >= R.out_step && step != last) write_output(step);
       }
-      if (step == last) write_output(step);
+      if (step == last) {
+        write_output(step);
+        if (structFact && bflbm_sf_samples(structFact) > 0) {  // structFact.WritePlotFile(step, time, root + "_SF", zero_avg = 1)
+          std::vector<double> re(pairA.size() * L.cells());
+          if (bflbm_sf_get(structFact, 1, re.data(), nullptr)) throw std::runtime_error("structure-factor accumulator: get failed");
+          const std::vector<std::string> hn = VariableNames(BFLBM_NHYDRO);
+          std::vector<std::string> names;
+          for (size_t q = 0; q < pairA.size(); ++q) names.push_back("struct_fact_real_" + hn[pairA[q]] + "_" + hn[pairB[q]]);
+          write_plotfile(concatenate(plot_file_root + "_SF", step, R.Ndigits), re, (int)pairA.size(), nx, ny, nz, names, step, step);
+          std::printf("structure factor: %lld samples written\n", bflbm_sf_samples(structFact));
+        }
+      }
     }
+    if (structFact) bflbm_sf_destroy(structFact);
     L.sync();
     const double loop_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
 

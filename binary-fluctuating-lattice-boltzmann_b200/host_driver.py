@@ -13,10 +13,11 @@ EXE = os.path.join(HERE, "bflbm_run_job")
 
 def build(force: bool = False) -> str:
     _build.build()
+    _build.build_sf()
     deps = [SRC] + [os.path.join(HERE, "csrc", "host", h) for h in ("bflbm.hpp", "parameters.hpp", "plotfile.hpp")]
     if not force and os.path.exists(EXE) and all(os.path.getmtime(d) <= os.path.getmtime(EXE) for d in deps):
         return EXE
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", SRC, "-o", EXE, "-L" + HERE, "-lbflbm", "-Wl,-rpath,$ORIGIN",
+    subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", SRC, "-o", EXE, "-L" + HERE, "-lbflbm_sf", "-lbflbm", "-Wl,-rpath,$ORIGIN",
                     "-Wl,-rpath-link," + HERE, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
     return EXE

@@ -109,6 +109,7 @@ def load_library() -> ctypes.CDLL:
         "bflbm_get_profile": (ip, [vp, vp, ctypes.POINTER(ctypes.c_longlong)]),
         "bflbm_kernel_launches": (ctypes.c_longlong, [vp]),
         "bflbm_device_bytes": (ctypes.c_size_t, [vp]),
+        "bflbm_get_dims": (ip, [vp] + [ctypes.POINTER(ip)] * 5),
         "bflbm_debug_philox": (ip, [vp, vp, vp]),
         "bflbm_last_error": (ctypes.c_char_p, []),
         "bflbm_version": (ctypes.c_char_p, []),

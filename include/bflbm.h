@@ -103,6 +103,9 @@ int bflbm_init_from_populations_slab(bflbm_lattice* h, const double* f_ghosted, 
 int bflbm_step(bflbm_lattice* h, int nsteps);
 int bflbm_sync(bflbm_lattice* h);
 long long bflbm_step_count(const bflbm_lattice* h);
+/* geom.Domain() of the lattice: local valid size, first global plane and global height (z0 = 0, nz_global = nz_local
+ * for a whole box).  Any pointer may be NULL. */
+int bflbm_get_dims(const bflbm_lattice* h, int* nx, int* ny, int* nz_local, int* z0, int* nz_global);
 
 /* fold/gold after the last step (post-stream populations): what the checkpoint writer reads,
  * main_run_job.cpp:399-409. */

@@ -24,6 +24,17 @@ def test_header_symbols_exported(bflbm):
     assert not missing, f"declared in include/bflbm.h but not exported: {missing}"
 
 
+def test_structure_factor_library_exports_its_header(bflbm):
+    bflbm.build_sf()
+    ctypes.CDLL(bflbm.LIB, mode=ctypes.RTLD_GLOBAL)
+    lib = ctypes.CDLL(bflbm.SF_LIB)
+    src = open(os.path.join(ROOT, "include", "bflbm_sf.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(bflbm_sf_[a-z0-9_]+)\s*\(", src)))
+    assert len(names) == 6
+    assert not [n for n in names if not hasattr(lib, n)]
+
+
 def test_python_binding_covers_header(bflbm):
     lib = bflbm.load_library()
     for n in declared_symbols():

@@ -84,10 +84,19 @@ plot_fields = hydrovars
     prm2 = tmp_path / "Parameters2"
     prm2.write_text(prm.read_text() + "\nkBT = 1e-6\nstep_continue = 20\nif_continue_from_last_frame = true\nnsteps = 10\nplot_int = 5\nt_window = 5\n"
                     .replace("kBT = 0.\n", ""))
-    txt = prm.read_text().replace("kBT = 0.", "kBT = 1e-6").replace("nsteps = 20", "nsteps = 10") + "step_continue = 20\nif_continue_from_last_frame = true\n"
+    txt = prm.read_text().replace("kBT = 0.", "kBT = 1e-6").replace("nsteps = 20", "nsteps = 10") + \
+        "step_continue = 20\nif_continue_from_last_frame = true\nplot_SF_window = 10\nout_SF_step = 5\n"
     prm2.write_text(txt)
     r2 = subprocess.run([exe, str(prm2)], capture_output=True, text=True)
     assert r2.returncode == 0, r2.stderr + r2.stdout
     run2 = base / "lbm_data_shshan_alpha0_1.50_xi_1.0e-06_size8-12-16_continue"
     names, h30 = read_plotfile(str(run2 / "plt0000030"))
     assert np.isfinite(h30).all() and abs(h30[0].sum() - O.hydrovars()[0].sum()) < 1e-9 * h30[0].sum()
+    # structure factors of the window [20, 30], every 5 steps (StructFact::WritePlotFile, main_run_job.cpp:50-54): 22 pairs on
+    # the shifted k grid, k = 0 zeroed, auto-correlations non-negative and inversion symmetric
+    assert "structure factor: 2 samples written" in r2.stdout
+    names, sf = read_plotfile(str(run2) + "/plt_SF0000030")
+    assert sf.shape == (22, 16, 12, 8) and names[0] == "struct_fact_real_rho_rho" and np.isfinite(sf).all()
+    assert sf[0, 8, 6, 4] == 0.0 and sf[0].min() >= 0.0 and sf[0].max() > 0.0
+    inv = np.roll(sf[0][::-1, ::-1, ::-1], 1, axis=(0, 1, 2))  # k -> -k on the shifted grid (even sizes)
+    assert np.allclose(inv, sf[0], rtol=1e-9, atol=1e-30)
