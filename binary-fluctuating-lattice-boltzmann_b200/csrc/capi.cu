@@ -415,14 +415,6 @@ int step_local(bflbm_lattice* h) {
   return rc;
 }
 
-// rebuilds R (with ghost planes) and the population ghost planes from X[cur] planes 1..nzl: whole box only
-int refresh_whole_box(bflbm_lattice* h) {
-  int rc;
-  if ((rc = wrap_population_ghosts(h, h->X[h->cur]))) return rc;
-  if ((rc = density_pass(h))) return rc;
-  return wrap_density_ghosts(h);
-}
-
 int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, int nzl, int device, bool whole, bflbm_lattice** out) {
   if (!out) return fail(BFLBM_ERR_ARG, "null out pointer");
   *out = nullptr;

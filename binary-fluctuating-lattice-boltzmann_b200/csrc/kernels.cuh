@@ -128,7 +128,8 @@ struct CopyList {
   int n;
   long long src[44], dst[44];  // offsets in doubles
 };
-__global__ void k_copy_planes(CopyList L, const double* __restrict__ src, double* __restrict__ dst, long long count) {
+// (src and dst may be the same array -- ghost-plane wrap inside one lattice -- so no __restrict__ here)
+__global__ void k_copy_planes(CopyList L, const double* src, double* dst, long long count) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const int j = blockIdx.y;

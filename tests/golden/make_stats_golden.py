@@ -7,7 +7,7 @@ The GPU tests (tests/test_gpu_statistics.py) run the same cases through the CUDA
 amrex::RandomNormal's stream is third-party and unpinned, so agreement is statistical by construction (SURVEY 8(c)).
 
 Run here (the container that has /root/reference):   python tests/golden/make_stats_golden.py [mixture|noise|capillary ...]
-Cases and cost on 8 host threads: mixture ~1 min, noise ~10 s, capillary ~20 min.
+Cases and cost on 8 host threads: mixture ~1 min, noise ~10 s, capillary ~20 min, droplet ~10 min.
 """
 import json
 import os
@@ -30,6 +30,8 @@ NOISE = dict(shape=(8, 8, 8), params=dict(kBT=1e-5, tau_f=0.5, tau_g=0.5, alpha0
              rho_lo=0.1, rho_hi=3.0, frames=200)
 CAPILLARY = dict(shape=(2, 32, 40), params=dict(kBT=1e-5, tau_f=0.5, tau_g=0.5, alpha0=1.5, alpha1=0.0, kappa=0.1),
                  rho_lo=0.1, rho_hi=3.0, frac=0.5, det_steps=3000, equil=10000, steps=150000, every=100)
+DROPLET = dict(shape=(24, 24, 24), params=dict(kBT=2e-5, tau_f=0.5, tau_g=0.5, alpha0=1.5, alpha1=0.0, kappa=0.1), radius=0.3,
+               rho_lo=0.1, rho_hi=3.0, det_steps=2000, equil=2000, steps=24000, every=40)
 SF_PAIRS = [(0, 0), (1, 1), (0, 1), (15, 15), (16, 16), (17, 17)]  # rho-rho, phi-phi, rho-phi, ub_a-ub_a
 
 
@@ -93,6 +95,32 @@ def run_capillary(stepper, rho_field, set_kbt, C=CAPILLARY):
             "gamma_lowk": stats.surface_tension_from_spectrum(k, p, C["params"]["kBT"], ny, nx, kmax=0.8)}
 
 
+def run_droplet(stepper, rho_field, set_kbt, C=DROPLET):
+    """configs[2] scaled down: deterministic relaxation of the droplet, then noise; relative principal axes of the
+    mass-weighted covariance every `every` steps; shape-mode sums of Droplet_Fluctuation.ipynb cells 22-25."""
+    set_kbt(0.0)
+    stepper(C["det_steps"])
+    ax_det = stats.droplet_axes(rho_field())
+    set_kbt(C["params"]["kBT"])
+    stepper(C["equil"])
+    ax = []
+    for _ in range(C["steps"] // C["every"]):
+        stepper(C["every"])
+        ax.append(stats.droplet_axes(rho_field()))
+    ax = np.array(ax)
+    plus, minus = stats.shape_mode_variances(ax)
+    return {"axes_det": ax_det.tolist(), "axes_mean": ax.mean(axis=0).tolist(), "axes_var": ax.var(axis=0).tolist(),
+            "sum_plus": plus, "sum_minus": minus, "frames": int(ax.shape[0])}
+
+
+def golden_droplet():
+    C = DROPLET
+    O = ref(C["shape"], dict(C["params"], kBT=0.0), 1234)
+    f, g = om.droplet_populations(*C["shape"], C["radius"], C["params"]["kappa"], C["rho_lo"], C["rho_hi"])
+    O.init_from_populations(f, g)
+    return run_droplet(O.step, lambda: O.hydrovars_bar()[0], lambda kbt: O.set_params(kBT=kbt))
+
+
 def golden_mixture():
     C = MIXTURE
     O = ref(C["shape"], C["params"], 20261018)
@@ -125,11 +153,11 @@ def golden_capillary():
 
 if __name__ == "__main__":
     om.build()
-    which = sys.argv[1:] or ["mixture", "noise", "capillary"]
+    which = sys.argv[1:] or ["mixture", "noise", "capillary", "droplet"]
     for name in which:
         t0 = time.time()
-        res = {"mixture": golden_mixture, "noise": golden_noise, "capillary": golden_capillary}[name]()
-        res["case"] = {"mixture": MIXTURE, "noise": NOISE, "capillary": CAPILLARY}[name]
+        res = {"mixture": golden_mixture, "noise": golden_noise, "capillary": golden_capillary, "droplet": golden_droplet}[name]()
+        res["case"] = {"mixture": MIXTURE, "noise": NOISE, "capillary": CAPILLARY, "droplet": DROPLET}[name]
         res["generator"] = "oracle/_ref (reference headers over oracle/shim, fast build, per-thread mt19937 streams)"
         res["seconds"] = time.time() - t0
         with open(os.path.join(HERE, f"stats_{name}.json"), "w") as fh:

@@ -10,6 +10,9 @@ What is followed (all `file:line` relative to /root/reference; yt / skimage / FH
   * noise covariance     NoiseCovariance.ipynb cell 3: time/ensemble variance of every dumped noise component divided by
                          the amplitude^2 of LBM_binary.H:113-127
   * equipartition        Mixture.ipynb cells 1-2: <d rho^2> cs2/kBT, <u_b^2>(rho+phi)/kBT, LB ("bar") velocities <u^2> rho/kBT
+  * droplet shape modes  LBM_hydrovs.H:258-335 (`fittingDropletCovariance`: mass-weighted covariance of rho about the centre of
+                         mass, eigenvalues) and Droplet_Fluctuation.ipynb cells 3, 22-25 (principal semi-axes
+                         a_i = lambda_i^(1/3) R / (lambda_j lambda_k)^(1/6); sums over i<j of <(da_i +- da_j)^2>)
   * interface height     Flat_Interface.ipynb cell 4 (`ih_direct`): iso-level (rho_lo+rho_hi)/2 of rho along z, UPPER
                          interface, linear interpolation between the two cells that bracket the level
   * capillary spectrum   Flat_Interface.ipynb cells 7, 9: h(y) of one x-slice, ensemble mean per y removed,
@@ -156,3 +159,28 @@ def surface_tension_from_spectrum(k, p, kBT, ny, nx=1, kmax=None):
     kx = 2 * np.pi * np.fft.fftfreq(nx)
     s = np.array([np.sum(1.0 / (kx ** 2 + ky ** 2)) for ky in k[m]])
     return float(np.mean(kBT * ny / nx * s / p[m]))
+
+
+# ------------------------------------------------------------------------------------------ droplet shape modes
+def droplet_axes(rho: np.ndarray) -> np.ndarray:
+    """LBM_hydrovs.H:258-335: eigenvalues of the mass-weighted covariance matrix of rho about its centre of mass (cell
+    centres at i + 1/2, unit cells), turned into RELATIVE principal semi-axes a_i / R = (lambda_i^2 / (lambda_j lambda_k))^(1/6)
+    (Droplet_Fluctuation.ipynb cell 3), ascending.  rho: (nz, ny, nx); the droplet must not straddle the periodic boundary."""
+    nz, ny, nx = rho.shape
+    z, y, x = np.meshgrid(np.arange(nz) + 0.5, np.arange(ny) + 0.5, np.arange(nx) + 0.5, indexing="ij")
+    m = rho.sum()
+    pos = np.stack([x, y, z])
+    com = (pos * rho).sum(axis=(1, 2, 3)) / m
+    d = pos - com[:, None, None, None]
+    cov = np.einsum("aijk,bijk,ijk->ab", d, d, rho) / m
+    lam = np.linalg.eigvalsh(cov)
+    return np.array([(lam[i] ** 2 / (lam[(i + 1) % 3] * lam[(i + 2) % 3])) ** (1.0 / 6.0) for i in range(3)])
+
+
+def shape_mode_variances(axes_frames: np.ndarray):
+    """Droplet_Fluctuation.ipynb cells 22-25 on relative axes s_i = a_i / R - 1 (frames, 3): the two sums that enter
+    gamma_(2,0) = 15 kBT / (16 pi R^2 sum_{i<j} <(s_i + s_j)^2>) and gamma_(2,+-2) = 45 kBT / (16 pi R^2 sum_{i<j} <(s_i - s_j)^2>)."""
+    s = np.asarray(axes_frames) - 1.0
+    plus = sum(((s[:, i] + s[:, j]) ** 2).mean() for i in range(3) for j in range(i + 1, 3))
+    minus = sum(((s[:, i] - s[:, j]) ** 2).mean() for i in range(3) for j in range(i + 1, 3))
+    return float(plus), float(minus)

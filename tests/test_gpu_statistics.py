@@ -129,3 +129,28 @@ def test_capillary_wave_spectrum(bflbm, oracle_mod):
     # k^-2 law of the capillary regime: k^2 <|h_k|^2> flat within 35 % over the three lowest modes
     flat = (k ** 2 * p)[:3]
     assert flat.max() / flat.min() < 1.35, flat
+
+
+def test_droplet_shape_mode_variance(bflbm, oracle_mod):
+    """configs[2] (Droplet_Fluctuation) scaled to 24^3: droplet r = 0.3, alpha0 = 1.5, kappa = 0.1, rho in [0.1, 3];
+    2000 deterministic steps, then kBT = 2e-5; every 40 steps the relative principal semi-axes of the mass-weighted
+    covariance of rho (LBM_hydrovs.H:258-335) for 24 000 steps; the two shape-mode sums of Droplet_Fluctuation.ipynb cells
+    22-25 against the reference code's (600 frames, shape modes decorrelate within ~10 frames: ~20 % sampling error each)."""
+    path = os.path.join(HERE, "golden", "stats_droplet.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/stats_droplet.json not generated")
+    G = _gold_module()
+    ref = _gold("droplet")
+    C = ref["case"]
+    C["shape"] = tuple(C["shape"])
+    f, g = oracle_mod.droplet_populations(*C["shape"], C["radius"], C["params"]["kappa"], C["rho_lo"], C["rho_hi"])
+    prm = dict(C["params"], kBT=0.0, rho_lo=C["rho_lo"], rho_hi=C["rho_hi"], seed=161803)
+    with bflbm.Lattice(*C["shape"], params=bflbm.Params(**prm)) as lat:
+        lat.init_from_populations(f, g)
+        got = G.run_droplet(lat.step, lambda: lat.hydrovars_bar()[0], lambda kbt: lat.set_params(kBT=kbt), C)
+    _record("droplet", got)
+    assert np.allclose(got["axes_det"], ref["axes_det"], rtol=1e-9, atol=0), "deterministic relaxation: same droplet shape"
+    assert np.abs(np.array(got["axes_mean"]) - np.array(ref["axes_mean"])).max() < 2e-3
+    for key in ("sum_plus", "sum_minus"):
+        ratio = got[key] / ref[key]
+        assert 0.6 < ratio < 1.6, f"{key}: GPU {got[key]:.3e} vs reference {ref[key]:.3e} (ratio {ratio:.2f})"
