@@ -51,6 +51,19 @@ def test_capillary_spectrum_recovers_planted_modes():
     assert abs(g / gamma - 1) < 0.1
 
 
+def test_droplet_axes_of_an_ellipsoid():
+    n = 40
+    z, y, x = np.meshgrid(*(np.arange(n) + 0.5 - n / 2,) * 3, indexing="ij")
+    sphere = ((x ** 2 + y ** 2 + z ** 2) < 9.0 ** 2).astype(float)
+    assert np.abs(stats.droplet_axes(sphere) - 1).max() < 2e-3
+    ell = (((x / 7) ** 2 + (y / 9) ** 2 + (z / 11) ** 2) < 1).astype(float)
+    want = np.array([7.0, 9.0, 11.0]) / (7.0 * 9.0 * 11.0) ** (1 / 3)
+    assert np.abs(stats.droplet_axes(ell) - want).max() < 0.01  # voxelised ellipsoid
+    frames = 1.0 + 1e-3 * np.array([[1, -1, 0], [-1, 1, 0], [0, 1, -1], [0, -1, 1.0]])
+    plus, minus = stats.shape_mode_variances(frames)
+    assert abs(plus - 2e-6) < 1e-12 and abs(minus - 6e-6) < 1e-12  # per frame: (0, 1, -1)^2 and (2, 1, -1)^2 x 1e-6
+
+
 def test_reference_statistics_satisfy_the_notebooks_expectations():
     m = _gold("mixture")
     n = np.prod(m["case"]["shape"])
