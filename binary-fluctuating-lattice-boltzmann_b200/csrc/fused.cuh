@@ -347,10 +347,10 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
           }
         }
         float n3[3], nbf[15];
-        {
+        if (RATE1) {
           double fg[Q], ff[Q];
-          // all 38 pulls are issued first; the random numbers of species f -- pure arithmetic on the cell's counter --
-          // are generated in their shadow, before the first loaded value is touched
+          // all 38 pulls are issued first; the cell's random numbers -- pure arithmetic on its counter -- are generated
+          // in their shadow, before the first loaded value is touched (only the conserved moments are needed: few registers)
 #pragma unroll
           for (int i = 0; i < Q; ++i) fg[i] = ld_off(XB.in[Q + i], off[i]);
 #pragma unroll
@@ -359,13 +359,23 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
           momentum_normals<NOISE>(nk, n3);
           mode_normals<NOISE, 0>(nk, nbf);
           mode_normals<NOISE, 1>(nk, nbg);
-          // species g: its non-conserved moments wait in shared memory while species f is processed (general rates)
           moments(fg, mg);
-          if (!RATE1) {
-#pragma unroll
-            for (int a = 4; a < Q; ++a) Sg[(a - 4) * NT + tid] = mg[a];
-          }
           moments(ff, mf);
+        } else {
+          // general rates: all 19 moments of both species are live, so the species are loaded one after the other, the
+          // non-conserved moments of g wait in shared memory while f is processed, and the normals are made when needed
+          double f[Q];
+#pragma unroll
+          for (int i = 0; i < Q; ++i) f[i] = ld_off(XB.in[Q + i], off[i]);
+          moments(f, mg);
+#pragma unroll
+          for (int a = 4; a < Q; ++a) Sg[(a - 4) * NT + tid] = mg[a];
+#pragma unroll
+          for (int i = 0; i < Q; ++i) f[i] = ld_off(XB.in[i], off[i]);
+          moments(f, mf);
+          nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
+          momentum_normals<NOISE>(nk, n3);
+          mode_normals<NOISE, 0>(nk, nbf);
         }
         collide_prepare<NOISE>(P, grho, gphi, n3, mf, mg, C);
         collide_species<NOISE, 0, RATE1>(P, nbf, C, mf);
@@ -388,6 +398,7 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
 #pragma unroll
           for (int a = 4; a < Q; ++a) mg[a] = Sg[(a - 4) * NT + tid];
         }
+        if (!RATE1) mode_normals<NOISE, 1>(nk, nbg);
         collide_species<NOISE, 1, RATE1>(P, nbg, C, mg);
       } else {
 #pragma unroll
