@@ -482,7 +482,7 @@ int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, 
     if (!whole) TRY(dev_alloc(h, &h->recv[s], h->halo_doubles));
   }
   h->diag_blocks = (size_t)h->grid_xy.x * h->grid_xy.y * nzl;
-  TRY(dev_alloc(h, &h->diag_partial, h->diag_blocks * 5));
+  TRY(dev_alloc(h, &h->diag_partial, h->diag_blocks * NDIAG));
   TRY(dev_alloc(h, &h->diag_count, (size_t)1));
   {
     const char* r1 = getenv("BFLBM_RATE1");
@@ -865,7 +865,7 @@ int bflbm_get_noise(bflbm_lattice* h, double* fn, double* gn) {
 }
 int bflbm_get_normals(bflbm_lattice* h, double* out33) { return observe<OBS_NORMALS>(h, BFLBM_NNORMALS, out33, false, true); }
 
-static int run_diag(bflbm_lattice* h, double sums[5], unsigned long long* bad) {
+static int run_diag(bflbm_lattice* h, double sums[NDIAG], unsigned long long* bad) {
   int rc = set_device(h);
   if (rc) return rc;
   if ((rc = ensure_full_R(h))) return rc;
@@ -873,19 +873,19 @@ static int run_diag(bflbm_lattice* h, double sums[5], unsigned long long* bad) {
   k_diag<<<cell_grid(h, h->G.nzl), h->block, 0, h->stream>>>(h->G, h->R, h->diag_partial, h->diag_count);
   ++h->launches;
   CU(cudaGetLastError());
-  std::vector<double> part(h->diag_blocks * 5);
+  std::vector<double> part(h->diag_blocks * NDIAG);
   CU(cudaMemcpyAsync(part.data(), h->diag_partial, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(bad, h->diag_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  for (int k = 0; k < 5; ++k) sums[k] = 0.;
+  for (int k = 0; k < NDIAG; ++k) sums[k] = 0.;
   for (size_t b = 0; b < h->diag_blocks; ++b)
-    for (int k = 0; k < 5; ++k) sums[k] += part[b * 5 + k];
+    for (int k = 0; k < NDIAG; ++k) sums[k] += part[b * NDIAG + k];
   return 0;
 }
 int bflbm_center_of_mass(bflbm_lattice* h, double* com3, double* sums4) {
   CHECK_H(h);
   if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
-  double s[5];
+  double s[NDIAG];
   unsigned long long bad;
   int rc = run_diag(h, s, &bad);
   if (rc) return rc;
@@ -896,12 +896,52 @@ int bflbm_center_of_mass(bflbm_lattice* h, double* com3, double* sums4) {
 int bflbm_total_mass(bflbm_lattice* h, double* mr, double* mp) {
   CHECK_H(h);
   if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
-  double s[5];
+  double s[NDIAG];
   unsigned long long bad;
   int rc = run_diag(h, s, &bad);
   if (rc) return rc;
   if (mr) *mr = s[0];
   if (mp) *mp = s[1];
+  return 0;
+}
+int bflbm_second_moments(bflbm_lattice* h, double* sums10) {
+  CHECK_H(h);
+  if (!sums10) return fail(BFLBM_ERR_ARG, "null output");
+  if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
+  double s[NDIAG];
+  unsigned long long bad;
+  int rc = run_diag(h, s, &bad);
+  if (rc) return rc;
+  sums10[0] = s[0];
+  for (int k = 1; k < 10; ++k) sums10[k] = s[k + 1];
+  return 0;
+}
+// eigenvalues of a symmetric 3x3 matrix {xx, yy, zz, xy, xz, yz}, ascending (trigonometric closed form)
+static void sym3_eigenvalues(const double c[6], double e[3]) {
+  const double p1 = c[3] * c[3] + c[4] * c[4] + c[5] * c[5];
+  const double q = (c[0] + c[1] + c[2]) / 3.;
+  const double p2 = (c[0] - q) * (c[0] - q) + (c[1] - q) * (c[1] - q) + (c[2] - q) * (c[2] - q) + 2. * p1;
+  if (p2 <= 0.) { e[0] = e[1] = e[2] = q; return; }
+  const double p = sqrt(p2 / 6.);
+  const double b[6] = {(c[0] - q) / p, (c[1] - q) / p, (c[2] - q) / p, c[3] / p, c[4] / p, c[5] / p};
+  const double det = b[0] * (b[1] * b[2] - b[5] * b[5]) - b[3] * (b[3] * b[2] - b[5] * b[4]) + b[4] * (b[3] * b[5] - b[1] * b[4]);
+  const double r = std::max(-1., std::min(1., det / 2.));
+  const double phi = acos(r) / 3.;
+  e[2] = q + 2. * p * cos(phi);
+  e[0] = q + 2. * p * cos(phi + 2. * M_PI / 3.);
+  e[1] = 3. * q - e[0] - e[2];
+}
+int bflbm_droplet_covariance(bflbm_lattice* h, double* com3, double* cov6, double* eig3) {
+  CHECK_H(h);
+  if (!h->whole_box) return fail(BFLBM_ERR_ARG, "slab lattice: combine bflbm_second_moments of all slabs instead");
+  double m[10];
+  int rc = bflbm_second_moments(h, m);
+  if (rc) return rc;
+  const double M = m[0], cx = m[1] / M, cy = m[2] / M, cz = m[3] / M;
+  const double c[6] = {m[4] / M - cx * cx, m[5] / M - cy * cy, m[6] / M - cz * cz, m[7] / M - cx * cy, m[8] / M - cx * cz, m[9] / M - cy * cz};
+  if (com3) { com3[0] = cx; com3[1] = cy; com3[2] = cz; }
+  if (cov6) for (int k = 0; k < 6; ++k) cov6[k] = c[k];
+  if (eig3) sym3_eigenvalues(c, eig3);
   return 0;
 }
 int bflbm_check_nan(bflbm_lattice* h, long long* count) {

@@ -2,7 +2,7 @@
 //
 // The reference's driver calls header-inline functions on caller-owned MultiFabs:
 //   LBM_init_mixture / LBM_init_stripe / LBM_init_droplet / LBM_init / LBM_timestep / LBM_hydrovars /
-//   LBM_hydrovars_density / thermal_noise / update_com      (LBM_binary.H:73-742, LBM_hydrovs.H:26-60)
+//   LBM_hydrovars_density / thermal_noise / update_com / fittingDropletCovariance   (LBM_binary.H:73-742, LBM_hydrovs.H:26-60, 258-335)
 // plus globals kBT, tau_f, tau_g, alpha0, alpha1, kappa, seed (LBM_d3q19.H:10, LBM_binary.H:17-30).
 // bflbm::Lattice bundles what those MultiFabs hold (device resident) and the free functions below keep the
 // reference's names and argument meaning, so a driver written against LBM_binary.H ports line by line.
@@ -87,6 +87,12 @@ inline std::array<double, 3> update_com(Lattice& L) {                           
   std::array<double, 3> c;
   check(bflbm_center_of_mass(L.handle(), c.data(), nullptr));
   return c;
+}
+// fittingDropletCovariance (LBM_hydrovs.H:258-335), one frame: eigenvalues (ascending) of the mass-weighted covariance of rho
+inline std::array<double, 3> fittingDropletCovariance(Lattice& L) {
+  std::array<double, 3> e;
+  check(bflbm_droplet_covariance(L.handle(), nullptr, nullptr, e.data()));
+  return e;
 }
 // MultiFabNANCheck (Debug.H:136-149): throws instead of exit(0)
 inline void MultiFabNANCheck(Lattice& L) {

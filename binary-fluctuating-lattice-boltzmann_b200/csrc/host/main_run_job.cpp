@@ -144,6 +144,8 @@ int main(int argc, char** argv) {
         if (R.system == "droplet") {
           const auto c = update_com(L);
           std::printf("Center of Mass: (%g,%g,%g)\n", c[0], c[1], c[2]);
+          const auto ev = fittingDropletCovariance(L);  // LBM_hydrovs.H:258-335 (shape-mode diagnostics)
+          std::printf("Covariance eigenvalues: (%.10g,%.10g,%.10g)\n", ev[0], ev[1], ev[2]);
         }
         if (step >= R.out_step && step != last) write_output(step);
       }

@@ -315,32 +315,39 @@ __global__ void __launch_bounds__(256) k_observe(Geom G, DevParams P, long long 
   }
 }
 
-// diagnostics: per-block partial sums {rho, phi, rho*x, rho*y, rho*zg} and count of non-finite hydro values
+// diagnostics: per-block partial sums {rho, phi, rho*x, rho*y, rho*zg, rho*xx, rho*yy, rho*zz, rho*xy, rho*xz, rho*yz}
+// (cell indices as coordinates; zg = global plane) and count of non-finite densities.  First moments: update_com
+// (LBM_hydrovs.H:26-60); second moments: the mass-weighted covariance of fittingDropletCovariance (LBM_hydrovs.H:258-335).
+constexpr int NDIAG = 11;
 __global__ void __launch_bounds__(256) k_diag(Geom G, const double2* __restrict__ R, double* __restrict__ partial,
                                                unsigned long long* __restrict__ nonfinite) {
-  __shared__ double sh[5][256];
+  __shared__ double sh[NDIAG][256];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zl = blockIdx.z;
-  double v[5] = {0., 0., 0., 0., 0.};
+  double v[NDIAG];
+#pragma unroll
+  for (int k = 0; k < NDIAG; ++k) v[k] = 0.;
   if (x < G.nx && y < G.ny) {
     const double2 r = R[(long long)(zl + 1) * G.plane + (long long)y * G.nx + x];
-    v[0] = r.x; v[1] = r.y; v[2] = r.x * x; v[3] = r.x * y; v[4] = r.x * (G.z0 + zl);
+    const double X = x, Y = y, Z = G.z0 + zl;
+    v[0] = r.x; v[1] = r.y; v[2] = r.x * X; v[3] = r.x * Y; v[4] = r.x * Z;
+    v[5] = v[2] * X; v[6] = v[3] * Y; v[7] = v[4] * Z; v[8] = v[2] * Y; v[9] = v[2] * Z; v[10] = v[3] * Z;
     if (!(isfinite(r.x) && isfinite(r.y))) atomicAdd(nonfinite, 1ull);
   }
 #pragma unroll
-  for (int k = 0; k < 5; ++k) sh[k][tid] = v[k];
+  for (int k = 0; k < NDIAG; ++k) sh[k][tid] = v[k];
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
     if (tid < s) {
 #pragma unroll
-      for (int k = 0; k < 5; ++k) sh[k][tid] += sh[k][tid + s];
+      for (int k = 0; k < NDIAG; ++k) sh[k][tid] += sh[k][tid + s];
     }
     __syncthreads();
   }
   if (tid == 0) {
     const long long b = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) partial[b * 5 + k] = sh[k][0];
+    for (int k = 0; k < NDIAG; ++k) partial[b * NDIAG + k] = sh[k][0];
   }
 }
 __global__ void k_count_nonfinite(const double* __restrict__ a, long long n, unsigned long long* __restrict__ cnt) {

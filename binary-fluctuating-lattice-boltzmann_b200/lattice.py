@@ -110,6 +110,8 @@ def load_library() -> ctypes.CDLL:
         "bflbm_kernel_launches": (ctypes.c_longlong, [vp]),
         "bflbm_device_bytes": (ctypes.c_size_t, [vp]),
         "bflbm_get_dims": (ip, [vp] + [ctypes.POINTER(ip)] * 5),
+        "bflbm_second_moments": (ip, [vp, vp]),
+        "bflbm_droplet_covariance": (ip, [vp, vp, vp, vp]),
         "bflbm_debug_philox": (ip, [vp, vp, vp]),
         "bflbm_last_error": (ctypes.c_char_p, []),
         "bflbm_version": (ctypes.c_char_p, []),
@@ -257,6 +259,13 @@ class Lattice:
         sums = (ctypes.c_double * 4)()
         _check(self.lib.bflbm_center_of_mass(self.h, com, sums))
         return np.array(com), np.array(sums)
+
+    def droplet_covariance(self):
+        """(com[3], cov[3, 3], eigenvalues[3] ascending) of rho: fittingDropletCovariance, LBM_hydrovs.H:258-335."""
+        com, c6, e = np.empty(3), np.empty(6), np.empty(3)
+        _check(self.lib.bflbm_droplet_covariance(self.h, com.ctypes.data, c6.ctypes.data, e.ctypes.data))
+        cov = np.array([[c6[0], c6[3], c6[4]], [c6[3], c6[1], c6[5]], [c6[4], c6[5], c6[2]]])
+        return com, cov, e
 
     def total_mass(self):
         a, b = ctypes.c_double(), ctypes.c_double()

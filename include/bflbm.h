@@ -128,6 +128,12 @@ int bflbm_get_populations_device(bflbm_lattice* h, double* dev_f, double* dev_g)
 /* update_com  LBM_hydrovs.H:26-60 (centre of mass of rho; local-slab partial sums:
  * sums4 = {mass, sum rho*x, sum rho*y, sum rho*z_global}). */
 int bflbm_center_of_mass(bflbm_lattice* h, double* com3, double* sums4);
+/* Raw material of the droplet shape diagnostics (fittingDropletCovariance, LBM_hydrovs.H:258-335): local-slab partial sums
+ * sums10 = {M, sum rho x, sum rho y, sum rho z_global, sum rho xx, yy, zz, xy, xz, yz} with cell indices as coordinates. */
+int bflbm_second_moments(bflbm_lattice* h, double* sums10);
+/* Whole box: centre of mass, mass-weighted covariance {xx, yy, zz, xy, xz, yz} of rho about it, and its eigenvalues in
+ * ascending order (what fittingDropletCovariance returns per frame; Eigen there, closed form here).  Any output may be NULL. */
+int bflbm_droplet_covariance(bflbm_lattice* h, double* com3, double* cov6, double* eig3);
 /* sums of rho and phi over the local cells (Debug.H:35-72 / main_run_job.cpp:224-228) */
 int bflbm_total_mass(bflbm_lattice* h, double* mass_rho, double* mass_phi);
 /* MultiFabNANCheck  Debug.H:136-149: counts non-finite values in the 22 hydro fields.

@@ -356,3 +356,54 @@ def test_rate1_fast_path_matches_general_path(bflbm, monkeypatch, kbt):
             fb, gb = B.populations()
             assert np.abs(fa - fb).max() <= 1e-14 * np.abs(fb).max()
             assert np.abs(ga - gb).max() <= 1e-14 * np.abs(gb).max()
+
+
+def test_droplet_covariance_matches_numpy(bflbm):
+    """fittingDropletCovariance (LBM_hydrovs.H:258-335) on the device: second moments by reduction, eigenvalues in
+    closed form, against numpy on the downloaded density (positions are cell indices; the covariance is shift invariant)."""
+    import stats
+    shape = (28, 20, 24)
+    prm = dict(kBT=0.0, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0)
+    with make_lattice(bflbm, shape, prm) as lat:
+        lat.init_droplet(0.25)
+        lat.step(7)
+        rho = lat.hydrovars_bar()[0]
+        com, cov, eig = lat.droplet_covariance()
+    nz, ny, nx = rho.shape
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    pos = np.stack([x, y, z]).astype(float)
+    m = rho.sum()
+    c = (pos * rho).sum(axis=(1, 2, 3)) / m
+    d = pos - c[:, None, None, None]
+    want = np.einsum("aijk,bijk,ijk->ab", d, d, rho) / m
+    assert np.allclose(com, c, rtol=1e-12)
+    assert np.abs(cov - want).max() <= 1e-10 * np.abs(want).max()
+    assert np.allclose(eig, np.linalg.eigvalsh(want), rtol=1e-9)
+    lam = eig
+    axes = np.array([(lam[i] ** 2 / (lam[(i + 1) % 3] * lam[(i + 2) % 3])) ** (1 / 6) for i in range(3)])
+    assert np.allclose(axes, stats.droplet_axes(rho), rtol=1e-9)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 2), (1, 7, 5), (3, 1, 4), (2, 2, 2), (33, 9, 3), (9, 17, 34)])
+@pytest.mark.parametrize("kbt", [0.0, 1e-5])
+def test_degenerate_and_ragged_boxes_vs_oracle(bflbm, oracle_mod, shape, kbt):
+    """Boxes thinner than the stencil, of width 1, odd, and not multiples of the 32 x 8 tile (partial bricks, bricks that
+    are their own periodic neighbours, no fold-in-staging): three steps against the CPU oracle, with injected normals."""
+    prm = dict(kBT=kbt, tau_f=0.6, tau_g=0.5, alpha0=1.5, alpha1=0.0, kappa=0.1, rho_lo=0.1, rho_hi=3.0)
+    with make_lattice(bflbm, shape, prm, seed=3) as lat:
+        lat.init_stripe(0.5)
+        f0, g0 = lat.populations()
+        O = oracle_mod.PortOracle(*shape)
+        O.set_params(**prm)
+        if kbt > 0:
+            O.set_normals(lat.normals())
+        O.init_from_populations(f0, g0)
+        for s in range(3):
+            lat.step(1)
+            if kbt > 0:
+                O.set_normals(lat.normals())
+            O.step(1)
+            fl, gl = lat.populations()
+            fo, go = O.populations()
+            assert rel_err(fl, fo) <= 10 * TOL and rel_err(gl, go) <= 10 * TOL, f"step {s}"
+            assert_hydro_close(lat.hydrovars(), O.hydrovars(), 10 * TOL, f"step {s}")
