@@ -153,7 +153,7 @@ def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res, sec_per_step = cpu_reference_run(a.cpu_size, 0, a.kbt)
+    res, sec_per_step = cpu_reference_run(a.cpu_size, a.cpu_steps, a.kbt)
     # K timed "steps", each a bounded sample: one LBM_timestep of the cpu_size^3 sample box
     from oracle import oracle as om
     line = {
