@@ -193,8 +193,23 @@ int main(int argc, char** argv) {
         ++frames;
       }
       if (frames > 0) {
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < 3; ++k)
           for (auto& v : mean[k]) v /= frames;
+        // PrintConvergence, p_tag = 1 (Debug.H:275-358): lattice mean of the frame-averaged |frame - ensemble mean|
+        std::vector<double> dev(3, 0.);
+        for (int s = std::max(step1, R.out_step); s <= step2; s += R.plot_int) {
+          if (s % R.plot_int != 0) continue;
+          PlotfileData F;
+          try { F = read_plotfile(concatenate(plot_file_root, s, R.Ndigits)); } catch (const std::exception&) { continue; }
+          for (int k = 0; k < 3; ++k) {
+            double a = 0.;
+            for (size_t i = 0; i < L.cells(); ++i) a += std::fabs(F.data[(size_t)comp_of[k] * L.cells() + i] - mean[k][i]);
+            dev[k] += a;
+          }
+        }
+        std::printf("Convergence test emsemble selection: from step %d to step %d with step interval %d\n", std::max(step1, R.out_step), step2, R.plot_int);
+        for (int k = 0; k < 3; ++k) {
+          std::printf("convergence L1 (%s): %.6e\n", nm[k], dev[k] / frames / (double)L.cells());
           write_plotfile(eq_name(nm[k]), mean[k], 1, nx, ny, nz, {std::string(nm[k]) + "_eq"}, 0, 0);
         }
         std::printf("equilibrium state: mean of %d frames in steps [%d, %d]\n", frames, step1, step2);

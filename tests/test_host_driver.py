@@ -80,6 +80,7 @@ plot_fields = hydrovars
     # equilibrium extraction: mean over frames 10..20
     _, rho_eq = read_plotfile(str(base / "equilibrium_rho_alpha0_1.50_size8-12-16"))
     assert rho_eq.shape == (1, 16, 12, 8)
+    assert "convergence L1 (rho):" in r.stdout and "equilibrium state: mean of 3 frames" in r.stdout  # PrintConvergence, Debug.H:275-358
     # restart from the checkpoint with noise on (two-stage workflow of ReadMe.ipynb cells 1-3)
     prm2 = tmp_path / "Parameters2"
     prm2.write_text(prm.read_text() + "\nkBT = 1e-6\nstep_continue = 20\nif_continue_from_last_frame = true\nnsteps = 10\nplot_int = 5\nt_window = 5\n"
