@@ -362,7 +362,7 @@ int launch_fused(bflbm_lattice* h, int rows, cudaStream_t st) {
 }
 
 // collide+stream of the slab and local density partials; leaves the outgoing messages packed
-int step_local(bflbm_lattice* h) {
+int step_local(bflbm_lattice* h, bool pack = true) {
   const bool noise = h->prm.kBT > 0.;
   mark(h, 0);
   int rc0 = 0;
@@ -410,7 +410,7 @@ int step_local(bflbm_lattice* h) {
   h->r_stale = partial;
   if ((rc = fold_local(h, partial ? 1 : 0))) return rc;
   mark(h, 2);
-  rc = pack_halo(h);
+  if (pack) rc = pack_halo(h);
   mark(h, 3);
   return rc;
 }
@@ -717,7 +717,7 @@ int bflbm_step(bflbm_lattice* h, int nsteps) {
   int rc = set_device(h);
   if (rc) return rc;
   for (int s = 0; s < nsteps; ++s) {
-    if ((rc = step_local(h))) return rc;
+    if ((rc = step_local(h, /*pack=*/false))) return rc;
     if (h->algo == 1) {
       if ((rc = wrap_population_ghosts(h, h->X[h->cur]))) return rc;
       mark(h, 2);  // two-pass: interval 2 = population ghost wrap, interval 1 -> density pass below
@@ -725,9 +725,10 @@ int bflbm_step(bflbm_lattice* h, int nsteps) {
       mark(h, 3);
       if ((rc = wrap_density_ghosts(h))) return rc;
     } else {
-      // periodic self-exchange: my lower neighbour is myself, so its message for me is my own side-1 message
-      double* const rv[2] = {h->send[1], h->send[0]};
-      if ((rc = unpack_halo(h, rv))) return rc;
+      // periodic self-exchange in one launch (what pack_halo + unpack_halo of my own messages would do)
+      k_wrap_whole_box<<<(unsigned)((h->G.plane + 255) / 256), 256, 0, h->stream>>>(h->G, h->X[h->cur], h->R);
+      ++h->launches;
+      CU(cudaGetLastError());
     }
     mark(h, 4);
     profile_collect(h);

@@ -559,6 +559,30 @@ __global__ void __launch_bounds__(256) k_density_partial(Geom G, const double* _
   R[I.zpl[1] + I.yrow[1] + x] = make_double2(rho, phi);
 }
 
+// Whole box on one GPU: the lattice is its own z-neighbour, so the halo step (pack x4, unpack x2, merge x2 for a slab) collapses
+// into ONE launch with the same arithmetic: ghost planes of the 5+5 populations that stream across the periodic face, and the
+// four density planes  R(1) <- R(1) + R(nzl+1),  R(0) <- R(nzl) + R(0),  R(nzl) <- R(nzl) + R(0),  R(nzl+1) <- R(1) + R(nzl+1)
+// (boundary = local + remote, ghost = remote + local: the operand order of k_merge_density_halo, hence bit-identical to slabs).
+// Matters for small lattices, where a step is launch bound (32^3: 10 launches of ~4 us against 25 us of kernel).
+__global__ void __launch_bounds__(256) k_wrap_whole_box(Geom G, double* X, double2* R) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G.plane) return;
+  const long long top = (long long)G.nzl * G.plane;
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      double* Xc = X + (long long)(s * Q + q) * G.comp + i;
+      if (cz(q) == 1) Xc[0] = Xc[top];                  // pulled from the plane below: ghost plane 0 <- plane nzl-1
+      if (cz(q) == -1) Xc[top + G.plane] = Xc[G.plane];  // ghost plane nzl <- plane 0
+    }
+  const double2 r0 = R[i], r1 = R[G.plane + i], rn = R[top + i], rn1 = R[top + G.plane + i];
+  R[G.plane + i] = make_double2(r1.x + rn1.x, r1.y + rn1.y);
+  R[i] = make_double2(rn.x + r0.x, rn.y + r0.y);
+  R[top + i] = make_double2(rn.x + r0.x, rn.y + r0.y);
+  R[top + G.plane + i] = make_double2(r1.x + rn1.x, r1.y + rn1.y);
+}
+
 // receiving side of the density part of a halo message:
 //   boundary plane:  R <- local + Ez(neighbour's contribution)      ghost plane:  R <- Pz(neighbour's local) + mine
 __global__ void k_merge_density_halo(long long plane, const double2* __restrict__ Pz, const double2* __restrict__ Ez,
