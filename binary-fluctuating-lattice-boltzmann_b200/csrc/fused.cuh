@@ -8,13 +8,16 @@
 // post-collision populations it has just produced into next-step densities:
 //     rho_{n+1}(y) = sum_i f*_i(y - c_i)
 //   - along x with warp shuffles, along y and z through a rolling 3-plane shared-memory accumulator;
-//   - contributions that leave the CTA's brick go to the brick's private one-cell shell ("extended box") in E;
-//   - k_fold then adds, in a fixed order, the <= 8 bricks whose extended boxes contain a cell.
-// No atomics, no zero-fill pass, bit-reproducible, and independent of how many GPUs the box is cut into
-// (as long as slab boundaries are brick boundaries).
-//
-// A CTA owns a brick of tx*ty columns and sweeps lz planes upward; the (rho, phi) neighbourhood needed
-// for the gradients is staged through a second rolling 3-plane shared-memory tile.
+//   - contributions that leave the CTA's brick go to the brick's private one-cell shell ("extended box") in E.
+// The NEXT step reads the boxes directly (fold-in-staging): a CTA owns a brick of tx*ty columns and sweeps lz planes
+// upward; the (rho, phi) neighbourhood needed for the gradients lives in a 4-plane shared-memory ring that is filled two
+// planes ahead with cp.async -- the brick's own extended plane is one contiguous copy, the entries that also lie in a
+// neighbouring brick's box fetch and add those 1 or 3 contributions in a fixed order.  Only the first / last plane of a
+// brick (two brick rows contribute) and the slab faces go through k_fold and R.
+// No atomics, no zero-fill pass, no separate density pass, bit-reproducible, and independent of how many GPUs the box
+// is cut into (as long as slab boundaries are brick boundaries).
+// Inside an iteration all 38 pulls are issued first and (rate-1 kernels) the cell's 33 normals are generated in their
+// shadow; the measured reasons for this shape, and what was tried instead, are in profiles/README.md.
 #pragma once
 #include "kernels.cuh"
 
