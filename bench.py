@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=E2E_STEPS)
-    ap.add_argument("--cpu-size", type=int, default=64)
+    ap.add_argument("--cpu-size", type=int, default=128, help="edge of the CPU arm's sample box (128^3: 2.6 GB, out of L3)")
     ap.add_argument("--cpu-steps", type=int, default=0, help="0 = sized for ~10-20 s")
     return ap.parse_args()
 
@@ -117,45 +117,68 @@ def measured_peak():
 
 
 # ----------------------------------------------------------------------------------------- CPU baseline
-def cpu_reference_run(size, steps, kbt):
-    """Times the reference's LBM_timestep on the host.  Returns dict for the `cpu_baseline` key."""
+def host_cores():
+    """Cores this process may use.  Deliberately NOT OMP_NUM_THREADS: torch.distributed.run exports OMP_NUM_THREADS=1 to
+    its workers, which in round 1 made the N >= 2 reference arm a 1-core run and the N = 1 arm an all-core run."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _cpu_oracle(size, kbt):
     from oracle import oracle as om
     om.build()
-    nthreads = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(nthreads))
+    prm = dict(kBT=kbt, tau_f=PARAMS["tau_f"], tau_g=PARAMS["tau_g"], alpha0=PARAMS["alpha0"], alpha1=0.0, kappa=PARAMS["kappa"])
     if om.RefOracle.available(fast=True):
         O = om.RefOracle(size, size, size, fast=True)
-        O.set_params(kBT=kbt, tau_f=PARAMS["tau_f"], tau_g=PARAMS["tau_g"], alpha0=PARAMS["alpha0"], alpha1=0.0, kappa=PARAMS["kappa"])
+        O.set_params(**prm)
         O.set_rng(2, 12345)  # per-thread mt19937 + std::normal_distribution behind amrex::RandomNormal
-        kind, cores = "reference", O.num_threads()
-    else:
-        O = om.PortOracle(size, size, size, fast=True)
-        O.set_params(kBT=kbt, tau_f=PARAMS["tau_f"], tau_g=PARAMS["tau_g"], alpha0=PARAMS["alpha0"], alpha1=0.0, kappa=PARAMS["kappa"],
-                     rho_lo=0.0, rho_hi=1.0)
-        kind, cores = "port", nthreads
-    O.init_mixture()
-    O.step(1)  # warm-up (page faults)
-    if steps <= 0:
+        return O, "reference", "reference headers (LBM_binary.H, LBM_d3q19.H) over oracle/shim, -O3 -march=x86-64-v3, OpenMP over the shim loops"
+    O = om.PortOracle(size, size, size, fast=True)
+    O.set_params(**prm, rho_lo=0.0, rho_hi=1.0)
+    return O, "port", "C port oracle/bflbm_oracle.c, -O3 -march=x86-64-v3, OpenMP"
+
+
+def cpu_reference_run(size, kbt, steps=0, warmup=1, budget_s=10.0):
+    """Times the reference's LBM_timestep on the host cores, twice: on ALL cores this process may use, and on ONE core
+    (the reference's shipped build is serial, GNUmakefile:16-19: that is the faithful figure).  Thread counts are set
+    explicitly through omp_set_num_threads.  steps = 0: sized for ~budget_s seconds.
+    Returns (cpu_baseline dict, seconds per all-core step)."""
+    O, kind, how = _cpu_oracle(size, kbt)
+    cells = size ** 3
+
+    def timed(nthreads, steps, warmup, budget):
+        O.set_num_threads(nthreads)
+        O.init_mixture()
         t0 = time.perf_counter()
-        O.step(1)
+        O.step(max(1, warmup))  # first step also takes the page faults
+        per = (time.perf_counter() - t0) / max(1, warmup)
+        if steps <= 0:
+            steps = int(max(1, min(400, budget / max(per, 1e-4))))
+        t0 = time.perf_counter()
+        O.step(steps)
         dt = time.perf_counter() - t0
-        steps = int(max(2, min(400, 12.0 / max(dt, 1e-4))))
-    t0 = time.perf_counter()
-    O.step(steps)
-    dt = time.perf_counter() - t0
-    mlups = size ** 3 * steps / dt / 1e6
-    return {"value": mlups, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"mixture {size}^3, kBT={kbt:g}, {steps} steps of LBM_timestep in {dt:.1f} s "
-                      f"({'reference headers over oracle/shim, -O3 -march=x86-64-v3, OpenMP' if kind == 'reference' else 'C port, -O3, OpenMP'})"}, dt / steps
+        return cells * steps / dt / 1e6, steps, dt
+
+    cores = host_cores()
+    v_all, n_all, dt_all = timed(cores, steps, warmup, budget_s)
+    v_one, n_one, dt_one = timed(1, 0, 1, budget_s / 2)
+    res = {"value": v_all, "unit": UNIT, "cores": cores, "kind": kind,
+           "one_core": {"value": v_one, "unit": UNIT, "cores": 1, "steps": n_one, "seconds": dt_one},
+           "sample": f"mixture {size}^3 ({cells * 154 * 8 / 1e9:.1f} GB of reference MultiFabs: out of cache like the real job), "
+                     f"kBT={kbt:g}; all {cores} cores: {n_all} steps of LBM_timestep in {dt_all:.1f} s; 1 core: {n_one} steps in {dt_one:.1f} s ({how})"}
+    O.close()
+    return res, dt_all / n_all
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res, sec_per_step = cpu_reference_run(a.cpu_size, a.cpu_steps, a.kbt)
-    # K timed "steps", each a bounded sample: one LBM_timestep of the cpu_size^3 sample box
-    from oracle import oracle as om
+    # K timed "steps" after W warm-up steps, each one LBM_timestep of the cpu_size^3 sample box, on all host cores;
+    # the same measurement at every --gpus N (the CPU arm does not depend on N)
+    res, sec_per_step = cpu_reference_run(a.cpu_size, a.kbt, steps=a.steps if a.cpu_steps <= 0 else a.cpu_steps, warmup=max(1, a.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -263,10 +286,20 @@ def run_b200(a):
                                                                      "unpack_or_wrap": per_kernel[3]},
                     "algorithmic_bytes_per_cell": BYTES_PER_CELL,
                     "step_frac_of_roofline": (BYTES_PER_CELL * cells_local / (ms / a.steps * 1e-3) / 1e9) / peak}
+        # DRAM bytes of one launch: an ncu capture of ONE configuration (profiles/traffic.json), not a measurement of this run.
+        # Reported only when this run is that configuration (same cells per GPU, kernel variant); otherwise null.
         tr = os.path.join(ROOT, "profiles", "traffic.json")
+        roofline["traffic_source"] = None
         if os.path.exists(tr):
             try:
-                roofline["traffic"] = json.load(open(tr)).get("bytes_per_launch")
+                t = json.load(open(tr))
+                same = (t.get("nx"), t.get("ny"), t.get("nz_local")) == (a.nx, a.ny, nzl) and bool(t.get("noise")) == (a.kbt > 0) and \
+                    t.get("algorithm", "fused") == a.algo and bool(t.get("rate1", True)) == (os.environ.get("BFLBM_RATE1", "1") != "0")
+                if same:
+                    roofline["traffic"] = t.get("bytes_per_launch")
+                    roofline["traffic_source"] = "ncu capture of this configuration, not of this run: " + str(t.get("source"))
+                else:
+                    roofline["traffic_source"] = "no ncu capture for this configuration"
             except Exception:
                 pass
 
@@ -277,7 +310,7 @@ def run_b200(a):
 
     cpu = None
     if rank == 0 and not a.no_cpu and world == 1:
-        cpu, _ = cpu_reference_run(a.cpu_size, a.cpu_steps, a.kbt)
+        cpu, _ = cpu_reference_run(a.cpu_size, a.kbt, steps=a.cpu_steps)
 
     if rank == 0:
         line = {

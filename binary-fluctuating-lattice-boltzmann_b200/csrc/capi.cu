@@ -109,13 +109,40 @@ cudaError_t for_each_fused(Fn fn) {
 #undef BFLBM_EACH
   return e;
 }
-// dynamic shared memory of the fused kernels for brick shape B (set for every variant: the choice is made at launch)
-cudaError_t set_fused_smem(const BrickGrid& B) {
-  auto set = [&](const void* k, bool rate1) {
-    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes(B, rate1));
-  };
-  cudaError_t e = for_each_fused<128>(set);
-  if (e == cudaSuccess) e = for_each_fused<256>(set);
+// Dynamic shared memory of the fused kernels.  The attribute is per FUNCTION and process-wide, not per lattice, so it is
+// set once to the largest need over every brick shape make_brick_grid can produce (tx = 8, 16, 32): lattices of different
+// shape or tau can then coexist.
+template <int NT>
+size_t fused_smem_max(bool rate1) {
+  size_t m = 0;
+  for (int tx = 8; tx <= 32; tx <<= 1) {
+    BrickGrid B{};
+    B.tx = tx; B.ty = NT / tx; B.ex = B.tx + 2; B.ey = B.ty + 2; B.pl = B.ex * B.ey;
+    m = std::max(m, fused_smem_bytes(B, rate1));
+  }
+  return m;
+}
+cudaError_t set_fused_smem() {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || (dev < 64 && done[dev])) return e;
+  e = for_each_fused<128>([&](const void* k, bool rate1) {
+    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_max<128>(rate1));
+  });
+  if (e == cudaSuccess)
+    e = for_each_fused<256>([&](const void* k, bool rate1) {
+      return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_max<256>(rate1));
+    });
+  // BFLBM_CARVEOUT=<percent of the SM's shared memory>: experiment knob (the driver otherwise sizes the carve-out to the
+  // resident CTAs' need; what is left of the 256 KB is L1)
+  if (const char* cv = getenv("BFLBM_CARVEOUT")) {
+    const int pct = atoi(cv);
+    auto setc = [&](const void* k, bool) { return cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct); };
+    if (e == cudaSuccess) e = for_each_fused<128>(setc);
+    if (e == cudaSuccess) e = for_each_fused<256>(setc);
+  }
+  if (e == cudaSuccess && dev < 64) done[dev] = true;
   return e;
 }
 
@@ -381,7 +408,11 @@ int step_local(bflbm_lattice* h, bool pack = true) {
   // the default kernel folds the brick-interior planes itself while staging (next step): only the brick faces here
   const bool partial = h->algo == 0 && h->fold_in_staging && fold_in_staging_ok(h->G, h->B);
   int rc;
-  if (!h->whole_box && h->overlap && !h->profiling && partial && h->B.bz >= 3) {
+  // The overlapped schedule needs a last brick row of at least two planes: with a single plane, the slab-face fold on
+  // `stream` would read the top shell of row bz-2 while `aux` is still writing it (and overwrite the R plane that row
+  // stages for its top gradients).  Such slabs take the single-stream path below.
+  const bool last_row_ok = h->G.nzl - (h->B.bz - 1) * h->B.lz >= 2;
+  if (!h->whole_box && h->overlap && !h->profiling && partial && h->B.bz >= 3 && last_row_ok) {
     // overlapped slab step.  stream: [first+last brick row] -> [fold of the 4 slab-face planes] -> [pack] -> caller's
     // exchange -> (step_end) unpack.  aux: [interior rows] -> [fold of the other brick faces], concurrent with the exchange.
     CU(cudaEventRecord(h->ev_prev, h->stream));          // everything queued so far (previous step, uploads, observers)
@@ -487,7 +518,7 @@ int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, 
   {
     const char* r1 = getenv("BFLBM_RATE1");
     h->rate1_fast_path = !(r1 && r1[0] == '0');
-    cudaError_t e = set_fused_smem(h->B);
+    cudaError_t e = set_fused_smem();
     if (e != cudaSuccess) { bflbm_destroy(h); return fail(BFLBM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
   }
 #undef TRY
@@ -662,7 +693,6 @@ int bflbm_set_tiling(bflbm_lattice* h, int brick_lz) {
     }
   }
   h->B = nb;
-  CU(set_fused_smem(nb));
   return 0;
 }
 

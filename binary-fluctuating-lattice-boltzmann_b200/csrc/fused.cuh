@@ -21,6 +21,29 @@
 #pragma once
 #include "kernels.cuh"
 
+// build-time experiment knobs of the general-rate kernels (see profiles/README.md)
+#ifndef BFLBM_G_NORMALS_EARLY
+#define BFLBM_G_NORMALS_EARLY 0
+#endif
+#ifndef BFLBM_PARK_F
+#define BFLBM_PARK_F 0
+#endif
+#ifndef BFLBM_PARK_G
+#define BFLBM_PARK_G 19
+#endif
+#ifndef BFLBM_G_MOMENT_SPACE   // 1: species g keeps its 15 non-conserved MOMENTS in shared memory (30 KB instead of 38 KB per CTA)
+#define BFLBM_G_MOMENT_SPACE 0
+#endif
+#ifndef BFLBM_F_MOMENT_SPACE   // 1: species f is relaxed in moment space in place (full forward transform, no f_old kept)
+#define BFLBM_F_MOMENT_SPACE 0
+#endif
+#ifndef BFLBM_GENERAL_SEQ      // 1: general rates load g, park it, then load f (fewer registers in flight)
+#define BFLBM_GENERAL_SEQ 0
+#endif
+#ifndef BFLBM_F_NORMALS_EARLY
+#define BFLBM_F_NORMALS_EARLY 1
+#endif
+
 namespace bflbm {
 
 struct BrickGrid {
@@ -59,7 +82,7 @@ inline size_t brick_doubles2(const BrickGrid& B) { return (size_t)B.brick * B.bx
 constexpr int FIX_SLOTS = 200;  // extra contributions of one extended plane: 2*(ex + ey) + 4*12 - ... <= 192 for ex*ey <= 2*NT
 inline size_t fused_smem_bytes(const BrickGrid& B, bool rate1) {
   return (size_t)7 * B.pl * sizeof(double2) + (size_t)B.pl * sizeof(int4) + (size_t)FIX_SLOTS * sizeof(double2) +
-         (rate1 ? 0 : (size_t)15 * B.tx * B.ty * sizeof(double));
+         (rate1 ? 0 : (size_t)((BFLBM_G_MOMENT_SPACE ? 15 : BFLBM_PARK_G) + BFLBM_PARK_F) * B.tx * B.ty * sizeof(double));
 }
 // fold-in-staging (the step kernel sums the brick contributions itself) needs every cell to lie in at most
 // 2 bricks per axis, i.e. no brick of width 1
@@ -152,8 +175,11 @@ inline PopBases make_pop_bases(const Geom& G, const double* X, double* Xn) {
   return P;
 }
 
+// Both kernels use the population-space form of the collision (physics.cuh): only the conserved moments of the incoming
+// state go through the forward transform, and the old populations enter as (1 - w) f_old after the inverse transform.
 // RATE1: both relaxation rates are exactly 1 (tau_f = tau_g = 1/2, the reference's shipped and only documented
-// setting): the incoming non-conserved moments are not needed (see relax_species), nothing of species g is parked.
+// setting): that term vanishes, nothing is kept.  General rates: f_old stays in registers, g_old is parked in shared memory.
+
 // FULL: nx and ny are multiples of the tile, every thread owns a cell (no activity predicates, no divergence code).
 template <bool NOISE, bool RATE1, bool FULL, int NT>
 __global__ void __launch_bounds__(NT, 512 / NT)
@@ -168,7 +194,10 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
   double2* A = smem + 4 * B.pl;   // [3][ey][ex] rolling accumulators of next-step (rho,phi)
   int4* Tab = reinterpret_cast<int4*>(smem + 7 * B.pl);     // [ey][ex] fold table: 3 extra sources + meta per entry
   double2* Fix = smem + 8 * B.pl;                           // [FIX_SLOTS] landing slots of the extra contributions
-  double* Sg = reinterpret_cast<double*>(Fix + FIX_SLOTS);  // [15][NT] parked moments 4..18 of species g (!RATE1)
+  double* So = reinterpret_cast<double*>(Fix + FIX_SLOTS);  // [19][NT] incoming populations of species g (!RATE1)
+  // rate-1 kernels make all 33 normals in the load shadow; the general kernels (19 more live doubles) make g's 15 late
+  constexpr int PARK_F = BFLBM_PARK_F, PARK_G = BFLBM_PARK_G;
+  constexpr bool G_NORMALS_EARLY = RATE1 || BFLBM_G_NORMALS_EARLY, F_NORMALS_EARLY = RATE1 || BFLBM_F_NORMALS_EARLY;
   __shared__ int nfix;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * B.tx + tx;
   const int x0 = blockIdx.x * B.tx, y0 = blockIdx.y * B.ty, zb = bZ * B.lz;
@@ -314,7 +343,9 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
     const bool left = tx == 0;
     {
       double mf[Q], mg[Q];
-      float nbg[15];
+      double fo[Q];  // incoming populations of species f: weight (1 - w_f) in the result (general rates only)
+      double gk[(BFLBM_G_MOMENT_SPACE ? 4 : Q - PARK_G) + 1];  // ... and the few of species g that do not wait in shared memory
+      float ybg[15];
       unsigned c = 0;  // byte offset of this cell inside a component
       CollideCtx C;
       NoiseKey nk;
@@ -349,45 +380,61 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
             off[i] = o;
           }
         }
-        float n3[3], nbf[15];
-        if (RATE1) {
-          double fg[Q], ff[Q];
+        float y3[3], ybf[15];
+        {
+          double go[Q];
           // all 38 pulls are issued first; the cell's random numbers -- pure arithmetic on its counter -- are generated
-          // in their shadow, before the first loaded value is touched (only the conserved moments are needed: few registers)
+          // in their shadow, before the first loaded value is touched
 #pragma unroll
-          for (int i = 0; i < Q; ++i) fg[i] = ld_off(XB.in[Q + i], off[i]);
+          for (int i = 0; i < Q; ++i) go[i] = ld_off(XB.in[Q + i], off[i]);
+          if (RATE1 || !BFLBM_GENERAL_SEQ) {
 #pragma unroll
-          for (int i = 0; i < Q; ++i) ff[i] = ld_off(XB.in[i], off[i]);
+            for (int i = 0; i < Q; ++i) fo[i] = ld_off(XB.in[i], off[i]);
+          }
           nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
-          momentum_normals<NOISE>(nk, n3);
-          mode_normals<NOISE, 0>(nk, nbf);
-          mode_normals<NOISE, 1>(nk, nbg);
-          moments(fg, mg);
-          moments(ff, mf);
-        } else {
-          // general rates: all 19 moments of both species are live, so the species are loaded one after the other, the
-          // non-conserved moments of g wait in shared memory while f is processed, and the normals are made when needed
-          double f[Q];
+          momentum_normals<NOISE>(nk, y3);
+          if (F_NORMALS_EARLY) mode_normals<NOISE, 0>(nk, ybf);
+          if (G_NORMALS_EARLY) mode_normals<NOISE, 1>(nk, ybg);
+          // only the conserved moments (density, momentum) of the incoming state are needed (physics.cuh, collide_species):
+          // the rest of the forward transform is dead code
+          moments(go, mg);
+          if (!RATE1) {  // general rates: the incoming state of g waits in shared memory while f is processed
+            if (BFLBM_G_MOMENT_SPACE) {
 #pragma unroll
-          for (int i = 0; i < Q; ++i) f[i] = ld_off(XB.in[Q + i], off[i]);
-          moments(f, mg);
+              for (int a = 4; a < Q; ++a) So[(a - 4) * NT + tid] = mg[a];
 #pragma unroll
-          for (int a = 4; a < Q; ++a) Sg[(a - 4) * NT + tid] = mg[a];
+              for (int a = 0; a < 4; ++a) gk[a] = mg[a];
+            } else {
 #pragma unroll
-          for (int i = 0; i < Q; ++i) f[i] = ld_off(XB.in[i], off[i]);
-          moments(f, mf);
-          nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
-          momentum_normals<NOISE>(nk, n3);
-          mode_normals<NOISE, 0>(nk, nbf);
+              for (int i = 0; i < PARK_G; ++i) So[i * NT + tid] = go[i];
+#pragma unroll
+              for (int i = PARK_G; i < Q; ++i) gk[i - PARK_G] = go[i];
+            }
+          }
+          if (!RATE1 && BFLBM_GENERAL_SEQ) {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) fo[i] = ld_off(XB.in[i], off[i]);
+          }
+          moments(fo, mf);
+          if (!RATE1) {  // ... and so do the first PARK_F incoming populations of f (register pressure at the inverse transform)
+#pragma unroll
+            for (int i = 0; i < PARK_F; ++i) So[(PARK_G + i) * NT + tid] = fo[i];
+          }
         }
-        collide_prepare<NOISE>(P, grho, gphi, n3, mf, mg, C);
-        collide_species<NOISE, 0, RATE1>(P, nbf, C, mf);
+        collide_prepare<NOISE>(P, grho, gphi, y3, mf, mg, C);
+        if (!F_NORMALS_EARLY) mode_normals<NOISE, 0>(nk, ybf);
+        collide_species<NOISE, 0, RATE1, !RATE1 && BFLBM_F_MOMENT_SPACE>(P, ybf, C, mf);
       } else {
 #pragma unroll
-        for (int i = 0; i < Q; ++i) mf[i] = 0.;
+        for (int i = 0; i < Q; ++i) mf[i] = fo[i] = 0.;
       }
       double p[Q];
       populations(mf, p);
+      if (!RATE1 && !BFLBM_F_MOMENT_SPACE) {
+        const double kf = keep_of(P, 0);
+#pragma unroll
+        for (int i = 0; i < Q; ++i) p[i] = fma(kf, (i < PARK_F && active) ? So[(PARK_G + i) * NT + tid] : fo[i], p[i]);
+      }
       if (active) {
 #pragma unroll
         for (int i = 0; i < Q; ++i) st_off(XB.out[i], c, p[i]);
@@ -397,17 +444,25 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
       ef[0] = left ? p[2] : p[1]; ef[1] = left ? p[10] : p[7]; ef[2] = left ? p[8] : p[9];
       ef[3] = left ? p[18] : p[15]; ef[4] = left ? p[16] : p[17];
       if (active) {
-        if (!RATE1) {
-#pragma unroll
-          for (int a = 4; a < Q; ++a) mg[a] = Sg[(a - 4) * NT + tid];
-        }
-        if (!RATE1) mode_normals<NOISE, 1>(nk, nbg);
-        collide_species<NOISE, 1, RATE1>(P, nbg, C, mg);
+        if (!G_NORMALS_EARLY) mode_normals<NOISE, 1>(nk, ybg);
+        collide_species<NOISE, 1, RATE1>(P, ybg, C, mg);
       } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) mg[i] = 0.;
       }
+      if (!RATE1 && BFLBM_G_MOMENT_SPACE && active) {  // moment space: m <- (1 - w) m_old + v, then one inverse transform
+        const double kg = keep_of(P, 1);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) mg[a] = fma(kg, gk[a], mg[a]);
+#pragma unroll
+        for (int a = 4; a < Q; ++a) mg[a] = fma(kg, So[(a - 4) * NT + tid], mg[a]);
+      }
       populations(mg, p);
+      if (!RATE1 && !BFLBM_G_MOMENT_SPACE && active) {
+        const double kg = keep_of(P, 1);
+#pragma unroll
+        for (int i = 0; i < Q; ++i) p[i] = fma(kg, i < PARK_G ? So[i * NT + tid] : gk[i - PARK_G], p[i]);
+      }
       if (active) {
 #pragma unroll
         for (int i = 0; i < Q; ++i) st_off(XB.out[Q + i], c, p[i]);

@@ -93,33 +93,31 @@ __global__ void __launch_bounds__(256) k_step_twopass(Geom G, DevParams P, long 
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zl = blockIdx.z;
   if (x >= G.nx || y >= G.ny) return;
   const CellIdx I = cell_idx(G, x, y, zl);
-  double mf[Q], mg[Q];
-  {
-    double f[Q];
-    pull19(X, G, I, f);
-    moments(f, mf);
-    pull19(X + (long long)Q * G.comp, G, I, f);
-    moments(f, mg);
-  }
+  double f[Q], g[Q], mf[Q], mg[Q];
+  pull19(X, G, I, f);
+  moments(f, mf);
+  pull19(X + (long long)Q * G.comp, G, I, g);
+  moments(g, mg);
   double grho[3], gphi[3];
   density_gradients(R, I, grho, gphi);
   const NoiseKey nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
   CollideCtx C;
-  float n3[3], nb[15];
-  momentum_normals<NOISE>(nk, n3);
-  collide_prepare<NOISE>(P, grho, gphi, n3, mf, mg, C);
+  float y3[3], yb[15];
+  momentum_normals<NOISE>(nk, y3);
+  collide_prepare<NOISE>(P, grho, gphi, y3, mf, mg, C);
   const long long c = I.zpl[1] + I.yrow[1] + x;
-  double f[Q];
-  mode_normals<NOISE, 0>(nk, nb);
-  collide_species<NOISE, 0>(P, nb, C, mf);
-  populations(mf, f);
+  double p[Q];
+  mode_normals<NOISE, 0>(nk, yb);
+  collide_species<NOISE, 0, false>(P, yb, C, mf);
+  populations(mf, p);
+  const double kf = keep_of(P, 0), kg = keep_of(P, 1);
 #pragma unroll
-  for (int i = 0; i < Q; ++i) Xn[(long long)i * G.comp + c] = f[i];
-  mode_normals<NOISE, 1>(nk, nb);
-  collide_species<NOISE, 1>(P, nb, C, mg);
-  populations(mg, f);
+  for (int i = 0; i < Q; ++i) Xn[(long long)i * G.comp + c] = fma(kf, f[i], p[i]);
+  mode_normals<NOISE, 1>(nk, yb);
+  collide_species<NOISE, 1, false>(P, yb, C, mg);
+  populations(mg, p);
 #pragma unroll
-  for (int i = 0; i < Q; ++i) Xn[(long long)(Q + i) * G.comp + c] = f[i];
+  for (int i = 0; i < Q; ++i) Xn[(long long)(Q + i) * G.comp + c] = fma(kg, g[i], p[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -234,7 +232,7 @@ __global__ void __launch_bounds__(256) k_observe(Geom G, DevParams P, long long 
     float n[36];
     cell_normals(nk, n);
 #pragma unroll
-    for (int d = 0; d < 33; ++d) out[o * 33 + d] = widen(n[d]);
+    for (int d = 0; d < 33; ++d) out[o * 33 + d] = normal_of(n[d]);
     return;
   }
   double f[Q], g[Q];
@@ -268,7 +266,7 @@ __global__ void __launch_bounds__(256) k_observe(Geom G, DevParams P, long long 
   if (NOISE) cell_normals(nk, n);
   else {
 #pragma unroll
-    for (int d = 0; d < 36; ++d) n[d] = 0.f;
+    for (int d = 0; d < 36; ++d) n[d] = NRM_BIAS_F;
   }
   if (MODE == OBS_NOISE) {
     // fnoisevs / gnoisevs (LBM_binary.H:113-127)
@@ -278,14 +276,14 @@ __global__ void __launch_bounds__(256) k_observe(Geom G, DevParams P, long long 
     out[(long long)Q * oc + o] = 0.;
 #pragma unroll
     for (int a = 1; a <= 3; ++a) {
-      const double v = aj * widen(n[a - 1]);
+      const double v = aj * normal_of(n[a - 1]);
       out[(long long)a * oc + o] = v;
       out[(long long)(Q + a) * oc + o] = -v;
     }
 #pragma unroll
     for (int a = 4; a < Q; ++a) {
-      out[(long long)a * oc + o] = (sqrt_bnorm(a) * sf) * widen(n[3 + 2 * (a - 4)]);
-      out[(long long)(Q + a) * oc + o] = (sqrt_bnorm(a) * sg) * widen(n[4 + 2 * (a - 4)]);
+      out[(long long)a * oc + o] = (sqrt_bnorm(a) * sf) * normal_of(n[3 + 2 * (a - 4)]);
+      out[(long long)(Q + a) * oc + o] = (sqrt_bnorm(a) * sg) * normal_of(n[4 + 2 * (a - 4)]);
     }
     return;
   }

@@ -7,7 +7,7 @@
 // through Philox4x32-10 (Salmon et al., SC'11) and a Box-Muller transform evaluated in fp32 with the
 // hardware fast paths (MUFU lg2/sin/cos); the amplitude multiply is done in fp64 by the caller.
 // Results therefore do not depend on the decomposition (number of GPUs, tiling) or launch order.
-// One 32-bit Philox word makes one Box-Muller PAIR: 22 bits for the radius uniform (|n| <= 5.7, 4 M levels),
+// One 32-bit Philox word makes one Box-Muller PAIR: 22 bits for the radius uniform (|n| <= 5.65, 4 M levels),
 // 10 bits for the angle (1024 equispaced rays: the marginal of r cos(theta) over M equispaced angles differs from
 // the continuous one only in Bessel terms J_M, J_2M, ... -- nothing below polynomial degree 1024).  That halves
 // the Philox work of the first version (32 + 32 bits per pair): 5 blocks per cell instead of 9.
@@ -63,24 +63,32 @@ __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.
 __device__ __forceinline__ float fast_sin(float x) { float r; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_cos(float x) { float r; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-// float -> double by integer re-packing (exponent re-bias, mantissa shift): exact for every normal float; the generator's
-// outputs are flush-to-zero, so the only other input is 0, which comes out as 2^-127 (5.9e-39 -- noise of that size is
-// nothing).  Why not cvt.f64.f32: the 33 conversions per cell go through the low-rate conversion unit (SASS F2F) and
-// cost 1.25 ms of a 17 ms step at 512^3 (measured by replacing them, profiles/README.md); these are 4 ALU operations.
-__device__ __forceinline__ double widen(float f) {
-  const unsigned u = __float_as_uint(f);
-  const unsigned hi = (((u & 0x7fffffffu) >> 3) + 0x38000000u) | (u & 0x80000000u);
-  return __hiloint2double((int)hi, (int)(u << 29));
+// The generator hands out every standard normal n in BIASED form  y = 1.5 + n / 16  (float, always inside [1, 2)): the bias costs nothing (it is the addend of the last fma of the Box-Muller transform; |n| <= 5.65) and makes the
+// float -> double widening two integer operations: sign 0 and exponent 0 are known, so the fp64 image of y is
+//     hi = (bits >> 3) + 0x38000000   (exponent re-bias + top 20 mantissa bits),   lo = bits << 29
+// -- exact.  The consumers never form n itself: amplitude * n = fma(16 amplitude, D, -24 amplitude) with D = widen_pos(y).
+// History: cvt.f64.f32 goes through the low-rate conversion unit (SASS F2F) and cost 1.25 ms of a 17 ms step at 512^3; a
+// general re-packing with sign handling is 5 ALU operations per normal, 165 per cell (round 1); this form is 66.
+constexpr float NRM_BIAS_F = 1.5f;
+constexpr double NRM_BIAS = 1.5;     // D = NRM_BIAS + n / NRM_SCALE
+constexpr double NRM_SCALE = 16.;
+__device__ __forceinline__ double widen_pos(float y) {  // exact for every positive normal float
+  const unsigned u = __float_as_uint(y);
+  return __hiloint2double((int)((u >> 3) + 0x38000000u), (int)(u << 29));
 }
+// the standard normal itself (observers, tests): exact, y has 24 significant bits
+__device__ __forceinline__ double normal_of(float y) { return NRM_SCALE * (widen_pos(y) - NRM_BIAS); }
 
-// one Philox word -> two independent standard normals
-__device__ __forceinline__ void box_muller(uint32_t w, float& n0, float& n1) {
+// one Philox word -> two independent standard normals, biased form
+__device__ __forceinline__ void box_muller(uint32_t w, float& y0, float& y1) {
   // U in (0,1): (w>>10 + 0.5) / 2^22 ; theta = 2 pi (w & 1023 + 0.5) / 1024 ; both conversions are exact in fp32
   const float U = fmaf((float)(w >> 10), 2.384185791015625e-07f, 1.1920928955078125e-07f);
-  const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(U));     // sqrt(-2 ln U), ln U = ln2 * lg2 U
+  // r / 16 = sqrt(-2 ln U) / 16 = sqrt(-(2 ln2 / 256) lg2 U).  lg2.approx of a U just below 1 may come out as +2^-22
+  // instead of -0: the |.| (a free operand modifier of MUFU.SQRT) keeps the argument non-negative.
+  const float r = fast_sqrt(fabsf(5.4152123481245727e-03f * fast_lg2(U)));
   const float th = fmaf((float)(w & 1023u), 6.1359231515425647e-03f, 3.0679615757712823e-03f);
-  n0 = r * fast_cos(th);
-  n1 = r * fast_sin(th);
+  y0 = fmaf(r, fast_cos(th), NRM_BIAS_F);
+  y1 = fmaf(r, fast_sin(th), NRM_BIAS_F);
 }
 
 // Philox counter layout: {cell_lo, cell_hi, step_lo, (step_hi & 0xffffff) | block << 24}, key = seed.

@@ -42,7 +42,8 @@ __device__ __forceinline__ void gradient19(const double (&n)[Q], double (&g)[3])
 }
 
 // 1/sqrt(x) for x > 0 to ~1 ulp: hardware seed (rsqrt.approx.f64 = MUFU.RSQ64H, ~2^-22) + two Newton steps.
-// No special-case code (the callers guard x = 0): 9 instructions instead of the ~15 + slow-path branch of sqrt() or 1/x.
+// No special-case code (the callers guard x = 0 and denormal x, which the .ftz seed flushes): 9 instructions instead of
+// the ~15 + slow-path branch of sqrt() or 1/x.
 __device__ __forceinline__ double rsqrt_pos(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -52,34 +53,43 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
   return y;
 }
 
-// n3: the first three standard normals of the cell (draws 0..2), ignored when !NOISE.
-// sq_rho / sq_phi return sqrt|rho|, sqrt|phi| (for the stress-mode noise amplitudes of collide_species).
+// y3: the first three standard normals of the cell (draws 0..2) in the generator's biased form (philox.cuh), ignored
+// when !NOISE.  sq_rho / sq_phi return sqrt|rho|, sqrt|phi| (for the stress-mode noise amplitudes of collide_species).
 // The three reciprocals (1/rho, 1/phi, 1/(rho+phi)) and three square roots the formulas need all come from three
 // reciprocal square roots: 1/x = sign(x) r^2, sqrt|x| = |x| r with r = rsqrt|x|  (each ~2 ulp; the bar is 1e-12).
 template <bool NOISE>
 __device__ __forceinline__ void cell_hydro(const DevParams& P, double rho, double phi, const double (&jf)[3], const double (&jg)[3],
-                                           const double (&grad_rho)[3], const double (&grad_phi)[3], const float (&n3)[3],
+                                           const double (&grad_rho)[3], const double (&grad_phi)[3], const float (&y3)[3],
                                            CellHydro& H, double& sq_rho, double& sq_phi) {
   H.rho = rho;
   H.phi = phi;
   const bool has_f = fabs(rho) > (double)FLT_EPSILON, has_g = fabs(phi) > (double)FLT_EPSILON;
   const double tot = rho + phi;
   const double ar = fabs(rho), ap = fabs(phi), at = fabs(tot);
-  const double rr = rsqrt_pos(ar), rp = rsqrt_pos(ap), rt = rsqrt_pos(at);
+  // rsqrt.approx flushes denormals to zero and hands back inf, which the Newton steps turn into NaN.  A denormal total
+  // density gives 1/(rho+phi) = inf here (the reference's division: > 4e307 or inf -- the run is lost either way); the
+  // square root of a denormal density (< 1.5e-154) is taken as 0.
+  const double rr = rsqrt_pos(ar), rp = rsqrt_pos(ap);
+  const double rt = at >= DBL_MIN ? rsqrt_pos(at) : __longlong_as_double(0x7ff0000000000000ll);
   const double inv_rho = has_f ? copysign(rr * rr, rho) : 0., inv_phi = has_g ? copysign(rp * rp, phi) : 0.;
   H.inv_tot = copysign(rt * rt, tot);  // unguarded, like the reference (LBM_binary.H:266-272, 286-288, 471): tot = 0 -> inf
-  sq_rho = ar > 0. ? ar * rr : 0.;
-  sq_phi = ap > 0. ? ap * rp : 0.;
-  double amp = 0.;
-  // sqrt(A kBT |rho phi / (rho + phi)|)  (LBM_binary.H:117) = sqrt(A kBT) sqrt|rho| sqrt|phi| / sqrt|rho + phi|
-  if (NOISE) amp = P.sqrt_amp_j * (sq_rho * sq_phi) * rt;
+  sq_rho = ar >= DBL_MIN ? ar * rr : 0.;
+  sq_phi = ap >= DBL_MIN ? ap * rp : 0.;
+  // xi = sqrt(A kBT |rho phi / (rho + phi)|) n  (LBM_binary.H:117), amplitude = sqrt(A kBT) sqrt|rho| sqrt|phi| / sqrt|rho + phi|,
+  // n = 16 (D - 1.5):  xi = fma(16 amp, D, -24 amp)
+  double amp16 = 0., ampb = 0.;
+  if (NOISE) {
+    const double amp = P.sqrt_amp_j * (sq_rho * sq_phi) * rt;
+    amp16 = NRM_SCALE * amp;
+    ampb = -(NRM_SCALE * NRM_BIAS) * amp;
+  }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     H.ufb[k] = jf[k] * inv_rho;
     H.ugb[k] = jg[k] * inv_phi;
     H.af[k] = has_f ? P.acc_coef * grad_phi[k] : 0.;
     H.ag[k] = has_g ? P.acc_coef * grad_rho[k] : 0.;
-    H.xi[k] = NOISE ? amp * widen(n3[k]) : 0.;
+    H.xi[k] = NOISE ? fma(amp16, widen_pos(y3[k]), ampb) : 0.;
     H.nfv[k] = H.xi[k] * inv_rho;
     H.ngv[k] = -H.xi[k] * inv_phi;
     const double d = (H.ufb[k] - H.ugb[k]) + 0.5 * (H.af[k] - H.ag[k]);
@@ -88,106 +98,122 @@ __device__ __forceinline__ void cell_hydro(const DevParams& P, double rho, doubl
   }
 }
 
-// m <- m + rate (meq(D, vb) - m) + Phi(D, u, a)   for one species (noise is added separately)
-// RATE1: the relaxation rate 1/(tau + 1/2) is exactly 1 (the reference's shipped tau = 1/2, LBM_binary.H:18-19):
-// every mode is reset to equilibrium + force, so the incoming non-conserved moments m[4..18] are never read and
-// the caller's forward transform shrinks to the conserved moments (dead-code elimination does the rest).
-template <bool RATE1 = false>
-__device__ __forceinline__ void relax_species(double rate, double pf, double D, const double (&vb)[3], const double (&u)[3],
-                                              const double (&a)[3], double (&m)[Q]) {
-  const double keep = 1. - rate;
-  const double Dr = RATE1 ? D : D * rate, Dp = D * pf;
-  auto upd = [&](int k, double v) { m[k] = RATE1 ? v : keep * m[k] + v; };
-  // momentum modes
-#pragma unroll
-  for (int k = 0; k < 3; ++k) upd(1 + k, Dr * vb[k] + Dp * a[k]);
-  // stress modes
-  const double vxx = vb[0] * vb[0], vyy = vb[1] * vb[1], vzz = vb[2] * vb[2];
-  const double axx = a[0] * u[0], ayy = a[1] * u[1], azz = a[2] * u[2];
-  const double tr = axx + ayy + azz;
-  upd(4, Dr * (vxx + vyy + vzz) + Dp * (2. * tr));
-  upd(5, Dr * (2. * vxx - vyy - vzz) + Dp * (6. * axx - 2. * tr));
-  upd(6, Dr * (vyy - vzz) + Dp * (2. * (ayy - azz)));
-  upd(7, Dr * (vb[0] * vb[1]) + Dp * (a[0] * u[1] + a[1] * u[0]));
-  upd(8, Dr * (vb[1] * vb[2]) + Dp * (a[1] * u[2] + a[2] * u[1]));
-  upd(9, Dr * (vb[0] * vb[2]) + Dp * (a[0] * u[2] + a[2] * u[0]));
-  // ghost modes: no equilibrium, no force
-#pragma unroll
-  for (int k = 10; k < Q; ++k) upd(k, 0.);
-}
-
-// Collision of one cell in moment space, split in three so that the caller can finish species f (inverse
-// transform, store) before touching species g:
+// Collision of one cell, split in two so that the caller can finish species f (inverse transform, store) before
+// touching species g:
 //   collide_prepare : hydro fields + barycentric velocity (needs the conserved moments of both species)
-//   collide_species : relaxation + forcing + noise of one species, in place
+//   collide_species : the part of the post-collision state that does not depend on the incoming non-conserved moments
+//
+// The reference relaxes EVERY moment with the same rate w = 1/(tau + 1/2) (LBM_binary.H:504-511):
+//     m_a <- (1 - w) m_a + w meq_a + Phi_a + noise_a ,   a = 0..18
+// and transforms back.  The transform is linear, so in population space
+//     f_i <- (1 - w) f_i + [M^-1 (w meq + Phi + noise)]_i
+// -- the forward transform is only needed for the conserved moments (densities and momenta) that meq, Phi and the noise
+// amplitudes are built from, for ANY tau, and the old populations enter through one fma each.  collide_species returns
+// v = w meq + Phi + noise; the caller adds (1 - w) f_old after the inverse transform.  With the reference's shipped
+// tau = 1/2 (LBM_binary.H:18-19) w = 1 and that term vanishes (RATE1 kernels never keep f_old).
 struct CollideCtx {
   CellHydro H;
   double vb[3];
   double sq_rho, sq_phi;  // sqrt|rho|, sqrt|phi|
 };
 
-// The standard normals come from the caller (momentum_normals / mode_normals below): n3 = the three momentum-mode
-// draws, nb = the 15 draws of modes 4..18 of the species.  Generating them is pure arithmetic on the cell's counter,
-// so the step kernel does it in the shadow of its population loads, before the first loaded value is needed.
+// The standard normals come from the caller (momentum_normals / mode_normals below) in biased form: y3 = the three
+// momentum-mode draws, yb = the 15 draws of modes 4..18 of the species.  Generating them is pure arithmetic on the cell's
+// counter, so the step kernel does it in the shadow of its population loads, before the first loaded value is needed.
 template <bool NOISE>
 __device__ __forceinline__ void collide_prepare(const DevParams& P, const double (&grad_rho)[3], const double (&grad_phi)[3],
-                                                const float (&n3)[3], const double (&mf)[Q], const double (&mg)[Q], CollideCtx& C) {
+                                                const float (&y3)[3], const double (&mf)[Q], const double (&mg)[Q], CollideCtx& C) {
   const double jf[3] = {mf[1], mf[2], mf[3]}, jg[3] = {mg[1], mg[2], mg[3]};
-  cell_hydro<NOISE>(P, mf[0], mg[0], jf, jg, grad_rho, grad_phi, n3, C.H, C.sq_rho, C.sq_phi);
+  cell_hydro<NOISE>(P, mf[0], mg[0], jf, jg, grad_rho, grad_phi, y3, C.H, C.sq_rho, C.sq_phi);
 #pragma unroll
   for (int k = 0; k < 3; ++k) C.vb[k] = (C.H.rho * C.H.uf[k] + C.H.phi * C.H.ug[k]) * C.H.inv_tot;  // LBM_binary.H:471
 }
 
-// SPECIES 0 = f (call first), 1 = g
-template <bool NOISE, int SPECIES, bool RATE1 = false>
-__device__ __forceinline__ void collide_species(const DevParams& P, const float (&nb)[15], CollideCtx& C, double (&m)[Q]) {
+// SPECIES 0 = f (call first), 1 = g.  v[0..18] = w meq(D, vb) + Phi(D, u, a) + noise (equilibrium LBM_binary.H:356-402,
+// forcing :404-449, noise :113-127).  rate = w; RATE1: w is exactly 1 (saves the multiplications by it).
+// INPLACE: v holds ALL 19 incoming moments and is relaxed in place, v_k <- (1 - w) v_k + (w meq + Phi + noise)_k -- the
+// moment-space form of the same update (one array instead of two: used where registers are short).
+template <bool NOISE, int SPECIES, bool RATE1, bool INPLACE = false>
+__device__ __forceinline__ void collide_species(const DevParams& P, const float (&yb)[15], const CollideCtx& C, double (&v)[Q]) {
   const CellHydro& H = C.H;
-  if (SPECIES == 0) relax_species<RATE1>(P.rate_f, P.force_pf, H.rho, C.vb, H.uf, H.af, m);
-  else              relax_species<RATE1>(P.rate_g, P.force_pf, H.phi, C.vb, H.ug, H.ag, m);
-  if (NOISE) {
+  const double D = SPECIES == 0 ? H.rho : H.phi, rate = SPECIES == 0 ? P.rate_f : P.rate_g;
+  const double (&u)[3] = SPECIES == 0 ? H.uf : H.ug;
+  const double (&a)[3] = SPECIES == 0 ? H.af : H.ag;
+  const double (&vb)[3] = C.vb;
+  const double Dr = RATE1 ? D : D * rate, Dp = D * P.force_pf;
+  // noise of mode k: sqrt(A kBT/cs2 b_k |D|) n = fma(amp16 sb_k, Dn, -1.5 amp16 sb_k), Dn = widen_pos(y)
+  const double s16 = NOISE ? NRM_SCALE * (P.sqrt_amp_s * (SPECIES == 0 ? C.sq_rho : C.sq_phi)) : 0.;
+  const double keep = 1. - rate;
+  auto old = [&](int k, double x) { return INPLACE ? fma(keep, v[k], x) : x; };
+  auto set = [&](int k, double eq, double force) {  // v_k = Dr eq + Dp force + noise_k
+    if (NOISE) {
+      const double amp = sqrt_bnorm(k) * s16;
+      v[k] = fma(amp, widen_pos(yb[k - 4]), fma(Dr, eq, fma(Dp, force, old(k, -NRM_BIAS * amp))));
+    } else {
+      v[k] = fma(Dr, eq, old(k, Dp * force));
+    }
+  };
+  v[0] = INPLACE ? D : Dr;  // keep D + w D
 #pragma unroll
-    for (int k = 0; k < 3; ++k) m[1 + k] += (SPECIES == 0 ? H.xi[k] : -H.xi[k]);
-    const double s = P.sqrt_amp_s * (SPECIES == 0 ? C.sq_rho : C.sq_phi);  // sqrt(A kBT/cs2 |density|), LBM_binary.H:125-126
+  for (int k = 0; k < 3; ++k) v[1 + k] = fma(Dr, vb[k], old(1 + k, Dp * a[k])) + (SPECIES == 0 ? H.xi[k] : -H.xi[k]);
+  const double vxx = vb[0] * vb[0], vyy = vb[1] * vb[1], vzz = vb[2] * vb[2];
+  const double axx = a[0] * u[0], ayy = a[1] * u[1], azz = a[2] * u[2];
+  const double tr = axx + ayy + azz;
+  set(4, vxx + vyy + vzz, 2. * tr);
+  set(5, 2. * vxx - vyy - vzz, 6. * axx - 2. * tr);
+  set(6, vyy - vzz, 2. * (ayy - azz));
+  set(7, vb[0] * vb[1], a[0] * u[1] + a[1] * u[0]);
+  set(8, vb[1] * vb[2], a[1] * u[2] + a[2] * u[1]);
+  set(9, vb[0] * vb[2], a[0] * u[2] + a[2] * u[0]);
+  // ghost modes: no equilibrium, no force
 #pragma unroll
-    for (int a = 4; a < Q; ++a) m[a] += (sqrt_bnorm(a) * s) * widen(nb[a - 4]);
+  for (int k = 10; k < Q; ++k) {
+    if (NOISE) {
+      const double amp = sqrt_bnorm(k) * s16;
+      v[k] = fma(amp, widen_pos(yb[k - 4]), old(k, -NRM_BIAS * amp));
+    } else {
+      v[k] = INPLACE ? keep * v[k] : 0.;
+    }
   }
 }
+// (1 - w) of the species: the weight of the old populations in the post-collision state
+__device__ __forceinline__ double keep_of(const DevParams& P, int species) { return 1. - (species == 0 ? P.rate_f : P.rate_g); }
 
 template <bool NOISE>
-__device__ __forceinline__ void momentum_normals(const NoiseKey& nk, float (&n3)[3]) {
-  float n0[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  if (NOISE) species_normals<0, 0, 4>(nk, n0);
-  n3[0] = n0[0]; n3[1] = n0[1]; n3[2] = n0[2];
+__device__ __forceinline__ void momentum_normals(const NoiseKey& nk, float (&y3)[3]) {
+  float y0[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (NOISE) species_normals<0, 0, 4>(nk, y0);
+  y3[0] = y0[0]; y3[1] = y0[1]; y3[2] = y0[2];
 }
 template <bool NOISE, int SPECIES>
-__device__ __forceinline__ void mode_normals(const NoiseKey& nk, float (&nb)[15]) {
+__device__ __forceinline__ void mode_normals(const NoiseKey& nk, float (&yb)[15]) {
   if (NOISE) {
     // modes 4..18 : normals F[3..17] (the pair F[2], F[3] comes from block 0, shared with the momentum draws) / G[0..14]
     constexpr int LO = SPECIES == 0 ? 2 : 0, HI = SPECIES == 0 ? 18 : 15;
     float t[HI - LO + 1];
     species_normals<SPECIES, LO, HI>(nk, t);
 #pragma unroll
-    for (int a = 4; a < Q; ++a) nb[a - 4] = t[mode_index(SPECIES, a) - LO];
+    for (int a = 4; a < Q; ++a) yb[a - 4] = t[mode_index(SPECIES, a) - LO];
   } else {
 #pragma unroll
-    for (int j = 0; j < 15; ++j) nb[j] = 0.f;
+    for (int j = 0; j < 15; ++j) yb[j] = 0.f;
   }
 }
 
 // the 33 standard normals of a cell in REFERENCE draw order (LBM_binary.H:115-127: a = 1..3 one draw each,
-// a = 4..18 two draws each, f then g) -- observer / test hook
-__device__ __forceinline__ void cell_normals(const NoiseKey& nk, float (&n)[36]) {
+// a = 4..18 two draws each, f then g), biased form -- observer / test hook
+__device__ __forceinline__ void cell_normals(const NoiseKey& nk, float (&y)[36]) {
   float F[19], G[16];
   species_normals<0, 0, 18>(nk, F);
   species_normals<1, 0, 15>(nk, G);
 #pragma unroll
-  for (int d = 0; d < 3; ++d) n[d] = F[d];
+  for (int d = 0; d < 3; ++d) y[d] = F[d];
 #pragma unroll
   for (int a = 4; a < Q; ++a) {
-    n[3 + 2 * (a - 4)] = F[mode_index(0, a)];
-    n[4 + 2 * (a - 4)] = G[mode_index(1, a)];
+    y[3 + 2 * (a - 4)] = F[mode_index(0, a)];
+    y[4 + 2 * (a - 4)] = G[mode_index(1, a)];
   }
-  n[33] = n[34] = n[35] = 0.f;
+  y[33] = y[34] = y[35] = NRM_BIAS_F;
 }
 
 }  // namespace bflbm

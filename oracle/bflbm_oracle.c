@@ -22,6 +22,9 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define NVEL 19
 
@@ -487,4 +490,18 @@ void oracle_constants(int* c57, double* w19, double* b19) {
     for (int d = 0; d < 3; ++d) c57[3 * i + d] = C[i][d];
     w19[i] = W[i]; b19[i] = B[i];
   }
+}
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }

@@ -156,6 +156,12 @@ class PortOracle(_Base):
         self._fn("set_params", None, [_dp] + [_d] * 8)(
             self.h, p["kBT"], p["tau_f"], p["tau_g"], p["alpha0"], p["alpha1"], p["kappa"], p["rho_lo"], p["rho_hi"])
 
+    def num_threads(self):
+        return self._fn("num_threads", _i, [])()
+
+    def set_num_threads(self, n):
+        self._fn("set_num_threads", None, [_i])(int(n))
+
     def set_normals(self, normals):
         """normals: (nz, ny, nx, 33) standard normals for the next noise generation, or None."""
         if normals is None:
@@ -215,6 +221,9 @@ class RefOracle(_Base):
 
     def num_threads(self):
         return self._fn("num_threads", _i, [])()
+
+    def set_num_threads(self, n):
+        self._fn("set_num_threads", None, [_i])(int(n))
 
 
 def stripe_populations(nx, ny, nz, frac, kappa, rho_lo, rho_hi):

@@ -164,4 +164,12 @@ int ref_num_threads() {
   return 1;
 #endif
 }
+// explicit thread count of the timing build (an OMP_NUM_THREADS=1 exported by a launcher must not decide the baseline)
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 }  // extern "C"

@@ -56,6 +56,12 @@ int main(int argc, char** argv) {
     PlotfileData C = read_plotfile(tmp + "/bflbm_test_chk");
     assert(C.ncomp == 19 && C.data == f && C.names[0] == "rho_chk");
     EXPECT_THROW(read_plotfile(tmp + "/does_not_exist"));
+    // multi-box files (what the reference writes from its max_grid_size decomposition, main_run_job.cpp:140-143): boxes of
+    // at most 2 cells per edge -> 3 x 2 x 2 = 12 FABs at increasing offsets, reassembled into the same global array
+    write_plotfile(tmp + "/bflbm_test_multibox", d, nc, nx, ny, nz, names, 7., 7, 2);
+    PlotfileData M = read_plotfile(tmp + "/bflbm_test_multibox");
+    assert(M.nboxes == 12 && M.nx == nx && M.ny == ny && M.nz == nz && M.step == 7);
+    assert(M.data == d);
   }
   std::puts("host_cpp_test ok");
   return 0;

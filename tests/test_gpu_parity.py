@@ -317,6 +317,33 @@ def test_slabs_bitwise_equal_to_whole_box(bflbm, nslabs, kbt, lz):
             S.close()
 
 
+def test_slabs_with_one_plane_last_brick_row(bflbm):
+    """nz_local % brick height == 1: the last brick row of every slab is a single plane.  The overlapped schedule would
+    race there (slab-face fold on the main stream against the interior rows on the second stream), so the library must
+    fall back to the single-stream step.  Slab boundaries are not brick boundaries of the whole box here, so agreement is at
+    rounding level rather than bitwise; a stale plane would show up at O(1e-3).  Run twice: same bits."""
+    from bflbm_b200.distributed import EmulatedSlabs
+    shape = (20, 12, 51)
+    prm = bflbm.Params(kBT=1e-5, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, tau_f=0.7, tau_g=0.55, seed=5)
+    with bflbm.Lattice(*shape, params=prm) as whole:
+        whole.set_tiling(4)
+        whole.init_droplet(0.3)
+        whole.step(6)
+        want = whole.hydrovars()
+    runs = []
+    for _ in range(2):
+        S = EmulatedSlabs(*shape, 3, params=prm, brick_lz=4)
+        try:
+            assert all(nzl % 4 == 1 for _, nzl in S.bounds)
+            S.init_droplet(0.3)
+            S.step(6)
+            runs.append(S.gather("hydrovars"))
+        finally:
+            S.close()
+    assert np.array_equal(runs[0], runs[1]), "slab step is not reproducible run to run"
+    assert_hydro_close(runs[0], want, 1e-11, "slabs with a one-plane last brick row")
+
+
 def test_slabs_restart_from_populations(bflbm, oracle_mod):
     """LBM_init (restart) on slabs: ghosted upload + halo refresh, then parity with the oracle."""
     from bflbm_b200.distributed import EmulatedSlabs

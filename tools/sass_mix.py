@@ -6,7 +6,7 @@ import re
 import subprocess
 import sys
 
-lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "binary-fluctuating-lattice-boltzmann_b200", "libbflbm.so")
+lib = os.environ.get("BFLBM_LIB") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "binary-fluctuating-lattice-boltzmann_b200", "libbflbm.so")
 pat = sys.argv[1]
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 cur, hist, lines = None, collections.Counter(), []
@@ -24,7 +24,7 @@ for ln in out.splitlines():
             op = t[1] if t[0].startswith("@") else t[0]
             hist[op.split(".")[0]] += 1
 print(sum(hist.values()), "instructions")
-for op, c in hist.most_common(40):
+for op, c in hist.most_common(80):
     print(f"{op:10s} {c}")
 if "--dump" in sys.argv:
     print("\n".join(lines))
