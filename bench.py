@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--algo", default="fused", choices=["fused", "twopass"])
     ap.add_argument("--kbt", type=float, default=PARAMS["kBT"])
     ap.add_argument("--brick-lz", type=int, default=0)
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: ghost exchange by peer-to-peer stores into CUDA-IPC-mapped mailboxes (default) or NCCL send/recv")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=E2E_STEPS)
@@ -220,12 +222,17 @@ def run_b200(a):
     stream = torch.cuda.Stream()  # a real (non-default) stream: the library launches on it and the events are recorded on it
     torch.cuda.set_stream(stream)
 
+    halo = None
+    slab_parity = None
     if world == 1:
         lat = b.Lattice(a.nx, a.ny, nzl, params=prm, device=local)
         stepper = lat
     else:
         from bflbm_b200.distributed import SlabLattice
-        stepper = SlabLattice(a.nx, a.ny, nz_global, params=prm, device=local)
+        # correctness evidence in the line itself: the very path that is about to be timed, on a small box, against the
+        # whole box stepped on this rank's GPU -- bitwise, noise on (untimed)
+        slab_parity, halo = slab_parity_check(b, np, torch, dist, local, a.halo)
+        stepper = SlabLattice(a.nx, a.ny, nz_global, params=prm, device=local, peer=(halo == "peer"))
         lat = stepper.lat
     lat.set_stream(stream.cuda_stream)
     lat.set_algorithm(a.algo)
@@ -269,6 +276,11 @@ def run_b200(a):
         nan_count = lat.check_nan()
     except b.BflbmError:
         nan_count = -1
+    mass = list(lat.total_mass())  # global species masses after the timed steps (conserved exactly: = cells for the mixture)
+    if world > 1:
+        mt = torch.tensor(mass, device="cuda", dtype=torch.float64)
+        dist.all_reduce(mt, op=dist.ReduceOp.SUM)
+        mass = [float(v) for v in mt.tolist()]
 
     # ---- dominant kernel alone: per-kernel events inside the library, same step count -------------------
     roofline = None
@@ -322,13 +334,63 @@ def run_b200(a):
                                    f"(BASELINE.json configs[{4 if a.scaling == 'weak' else 3}])",
                        "cells_per_gpu": cells_local, "algorithm": a.algo, "parallelism": f"z-slabs x{world}",
                        "l2": "working set (two lattices, %.1f GB per GPU) far exceeds the 126 MB L2; no flush needed" % (lat.device_bytes / 1e9),
-                       "nonfinite_after_run": nan_count},
+                       "nonfinite_after_run": nan_count, "mass_rho": mass[0], "mass_phi": mass[1], "cells": cells,
+                       "halo": None if world == 1 else ("peer-to-peer stores into CUDA-IPC-mapped mailboxes, device-side flags (no collective per step)"
+                                                        if halo == "peer" else "NCCL send/recv (torch.distributed)"),
+                       "slab_parity": slab_parity},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def slab_parity_check(b, np, torch, dist, local, want):
+    """Slabs over the ranks of this job vs the whole box on one GPU: every rank compares its slab bit for bit after 12
+    fluctuating steps and a restart.  Also decides the halo transport: peer-to-peer stores through CUDA-IPC-mapped mailboxes
+    (default), NCCL send/recv if the mapping is refused (or --halo nccl)."""
+    from bflbm_b200.distributed import SlabLattice
+    world = dist.get_world_size()
+    nx, ny, nz, lz = 64, 48, 16 * world, 4
+    prm = b.Params(kBT=1e-5, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, tau_f=0.5, tau_g=0.5, seed=4711)
+    halo = want
+    S = None
+    if halo == "peer":
+        ok_here = 1
+        try:
+            S = SlabLattice(nx, ny, nz, params=prm, device=local, peer=True)
+        except b.BflbmError:
+            ok_here = 0
+        t = torch.tensor([ok_here], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 0:
+            halo = "nccl"
+            if S is not None:
+                S.lat.close()
+            S = None
+    if S is None:
+        S = SlabLattice(nx, ny, nz, params=prm, device=local, peer=False)
+    S.lat.set_tiling(lz)
+    S.init_droplet(0.3)
+    ok = True
+    with b.Lattice(nx, ny, nz, params=prm, device=local) as whole:
+        whole.set_tiling(lz)
+        whole.init_droplet(0.3)
+        sl = slice(S.z0, S.z0 + S.nzl)
+        for _ in range(3):
+            S.step(4)
+            whole.step(4)
+            ok &= bool(np.array_equal(whole.hydrovars()[:, sl], S.lat.hydrovars()))
+        fw, gw = whole.populations()
+        fs, gs = S.lat.populations()
+        ok &= bool(np.array_equal(fw[:, sl], fs) and np.array_equal(gw[:, sl], gs))
+    if halo == "peer":
+        ok &= S.lat.halo_error() == 0
+    S.lat.close()
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return ("bitwise" if int(t.item()) == 1 else "MISMATCH"), halo
 
 
 def run_e2e(a, b, np, torch, lat, stepper, world, cells, cells_local):

@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbflbm.so")
-SOURCES = ["capi.cu"]
+SOURCES = ["capi.cu", "multi.cu"]
 HEADERS = ["d3q19.cuh", "philox.cuh", "physics.cuh", "kernels.cuh", "fused.cuh"]
 
 NVCC_FLAGS = [

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
@@ -46,6 +47,8 @@ struct bflbm_lattice {
   bool whole_box = true;
   bool initialized = false;
   int algo = 0;  // 0 fused one-pass, 1 two-pass
+  bool algo_auto = true;  // nobody asked for an algorithm or a tiling: small whole boxes (L2 resident, launch / latency bound) use
+                          // the thread-per-cell two-pass kernels, everything else the fused brick kernel
   int lz_request = 0;
   int cta_threads = 256;  // threads per CTA of the fused kernel (BFLBM_CTA_THREADS=128|256)
   bool rate1_fast_path = true;  // use the rate == 1 specialisation when tau_f = tau_g = 1/2 (BFLBM_RATE1=0 disables it)
@@ -74,10 +77,15 @@ struct bflbm_lattice {
   bool r_stale = false;        // R is current only on brick-face planes; k_fold<2>(E[ecur]) completes it on demand
   bool fold_in_staging = true; // BFLBM_FOLD_IN_STAGING=0: separate full fold pass every step (first design)
 
-  // halo messages (slab) : [side] ; layout see pack_halo()
+  // halo messages : [side] ; layout see pack_halo().  recv[] = parity-0 slots of the mailbox (caller-driven exchange)
   double* send[2] = {nullptr, nullptr};
   double* recv[2] = {nullptr, nullptr};
   size_t halo_doubles = 0;
+  double* mailbox = nullptr;                  // see "halo messages" below
+  double* peer_base[2] = {nullptr, nullptr};  // the neighbours' mailboxes as seen from this GPU
+  bool peer_mode = false;
+  unsigned long long halo_seq = 0;
+  std::vector<std::string> ipc_keys;  // CUDA-IPC mappings this lattice holds a reference to
 
   // staging for host transfers and diagnostics
   double* stage = nullptr;
@@ -88,12 +96,26 @@ struct bflbm_lattice {
 
   dim3 block, grid_xy;  // thread-per-cell kernels: grid = (grid_xy.x, grid_xy.y, planes)
 
+  // CUDA graphs of K consecutive whole-box steps (launch-bound small lattices: Parameters:1-37 runs 32^3 .. 8x256x64 boxes
+  // for 1e5..1e6 steps).  Key = (K, cur, ecur); the step counter of the noise key lives in device memory (d_step) so that a
+  // captured chunk can be replayed; d_step_host mirrors the value it will have once everything queued has run.
+  bool use_graphs = true;  // BFLBM_GRAPH=0 disables
+  std::map<long long, cudaGraphExec_t> graphs;
+  long long* d_step = nullptr;
+  long long d_step_host = -1;
+  bool in_graph_capture = false;
+  int graph_step_off = 0, graph_bump = 0;
+  bool wrapped_in_fold = false;
+  bool ghosts_stale = false;  // two-pass steps leave the ghost planes of X and R behind
+
   // optional per-kernel timing: events ev[0..4] bracket {step kernel, fold, pack, unpack}
   bool profiling = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   double prof_ms[4] = {0., 0., 0., 0.};
   long long prof_steps = 0;
 };
+
+void release_ipc(bflbm_lattice* h);  // defined next to the peer API
 
 namespace {
 
@@ -264,77 +286,86 @@ int wrap_density_ghosts(bflbm_lattice* h) {
   CU(cudaGetLastError());
   return 0;
 }
-int density_pass(bflbm_lattice* h) {
-  k_density<<<cell_grid(h, h->G.nzl), h->block, 0, h->stream>>>(h->G, h->X[h->cur], h->R);
+// ---- halo messages ------------------------------------------------------------------------------------
+// Layout and protocol: fused.cuh (HaloPack / HaloUnpack).  SURVEY.md 8(e) option (ii), folded into a single message of
+// 112 B per face cell per neighbour.  One pack launch and one unpack launch per step.
+//
+// Mailbox (one cudaMalloc per slab lattice, so that ONE CUDA-IPC handle exports it):
+//   double recv[2 parities][2 sides][14 * plane]   incoming messages, double buffered by sequence parity
+//   u64    flag[2 sides]                           sequence number of the newest complete message per side
+//   u32    done, i32 err                           CTA counter of my pack kernel; set by a timed-out wait
+// Peer mode (bflbm_peer_connect*): my message for the neighbour on `side` is written by the pack kernel straight into
+// THAT lattice's recv[seq & 1][1 - side], then its flag[1 - side] <- seq.  Why two parities are enough: I overwrite a
+// slot at exchange q + 2, after my wait for q + 1 has seen the neighbour's pack q + 1, which follows its unpack q on
+// its stream.
+size_t mailbox_recv_doubles(const bflbm_lattice* h) { return (size_t)4 * h->halo_doubles; }
+size_t mailbox_bytes(const bflbm_lattice* h) { return mailbox_recv_doubles(h) * sizeof(double) + 64; }
+double* mailbox_recv(double* base, const bflbm_lattice* h, int parity, int side) { return base + (size_t)(parity * 2 + side) * h->halo_doubles; }
+unsigned long long* mailbox_flag(double* base, const bflbm_lattice* h, int side) {
+  return reinterpret_cast<unsigned long long*>(base + mailbox_recv_doubles(h)) + side;
+}
+unsigned int* mailbox_done(double* base, const bflbm_lattice* h) { return reinterpret_cast<unsigned int*>(mailbox_flag(base, h, 0) + 2); }
+int* mailbox_err(double* base, const bflbm_lattice* h) { return reinterpret_cast<int*>(mailbox_done(base, h) + 1); }
+
+int pack_halo(bflbm_lattice* h) {
+  const Geom& G = h->G;
+  HaloPack P{};
+  ++h->halo_seq;
+  const int parity = (int)(h->halo_seq & 1);
+  for (int side = 0; side < 2; ++side) {
+    const int want = side == 0 ? -1 : 1;  // side 0: c_z = -1 of plane 0;  side 1: c_z = +1 of plane nzl-1
+    const long long bplane = side == 0 ? 1 : G.nzl;  // storage index of my boundary plane
+    int n = 0;
+    for (int s = 0; s < 2; ++s)
+      for (int i = 0; i < Q; ++i)
+        if (cz(i) == want) P.pop_src[side][n++] = (long long)(s * Q + i) * G.comp + bplane * G.plane;
+    // density partial planes: Pz = R[boundary], Ez = R[outside ghost] (local sums written by the fold)
+    P.r_bnd[side] = 2 * bplane * G.plane;
+    P.r_out[side] = 2 * (side == 0 ? 0 : (long long)(G.nzl + 1)) * G.plane;
+    if (h->peer_mode) {
+      P.dst[side] = mailbox_recv(h->peer_base[side], h, parity, 1 - side);
+      P.flag[side] = mailbox_flag(h->peer_base[side], h, 1 - side);
+    } else {
+      P.dst[side] = h->send[side];
+      P.flag[side] = nullptr;
+    }
+  }
+  P.seq = h->halo_seq;
+  P.done = mailbox_done(h->mailbox, h);
+  const dim3 grid((unsigned)((G.plane + 255) / 256), 14, 2);
+  k_pack_halo<<<grid, 256, 0, h->stream>>>(P, h->X[h->cur], (const double*)h->R, G.plane);
   ++h->launches;
   CU(cudaGetLastError());
   return 0;
 }
-
-// ---- halo messages ------------------------------------------------------------------------------------
-// message to the neighbour on `side` (0: lower z, 1: upper z), in doubles:
-//   [10][plane]   the 5+5 populations of my boundary plane that the neighbour pulls across the face
-//                 (side 0: c_z = -1 of plane 0;  side 1: c_z = +1 of plane nzl-1)
-//   [2*plane]     Pz: my local partial (rho,phi) sums on my boundary plane
-//   [2*plane]     Ez: my contribution to (rho,phi) on the neighbour's boundary plane
-// (SURVEY.md 8(e) option (ii), folded into a single message: 112 B per face cell.)
-int pack_halo(bflbm_lattice* h) {
-  const Geom& G = h->G;
-  for (int side = 0; side < 2; ++side) {
-    CopyList L;
-    L.n = 0;
-    const int want = side == 0 ? -1 : 1;
-    const long long bplane = side == 0 ? 1 : G.nzl;  // storage index of my boundary plane
-    for (int s = 0; s < 2; ++s)
-      for (int i = 0; i < Q; ++i)
-        if (cz(i) == want) {
-          L.src[L.n] = (long long)(s * Q + i) * G.comp + bplane * G.plane;
-          L.dst[L.n] = (long long)L.n * G.plane;
-          ++L.n;
-        }
-    const int T = 256;
-    dim3 grid((unsigned)((G.plane + T - 1) / T), L.n);
-    k_copy_planes<<<grid, T, 0, h->stream>>>(L, h->X[h->cur], h->send[side], G.plane);
-    ++h->launches;
-    // density partial planes: Pz = R[boundary], Ez = R[outside ghost] (local sums written by the fold)
-    CopyList D;
-    D.n = 2;
-    D.src[0] = 2 * bplane * G.plane;                                  D.dst[0] = 10 * G.plane;
-    D.src[1] = 2 * (side == 0 ? 0 : (long long)(G.nzl + 1)) * G.plane; D.dst[1] = 12 * G.plane;
-    dim3 gridd((unsigned)((2 * G.plane + T - 1) / T), D.n);
-    k_copy_planes<<<gridd, T, 0, h->stream>>>(D, (const double*)h->R, h->send[side], 2 * G.plane);
-    ++h->launches;
-  }
-  CU(cudaGetLastError());
-  return 0;
-}
-// recv[side] holds the message the neighbour on `side` packed for me (its side 1-side message)
+// recv[side] holds the message the neighbour on `side` packed for me (its side 1-side message); peer mode reads the mailbox
 int unpack_halo(bflbm_lattice* h, double* const recv[2]) {
   const Geom& G = h->G;
+  HaloUnpack U{};
+  const int parity = (int)(h->halo_seq & 1);
   for (int side = 0; side < 2; ++side) {
-    CopyList L;
-    L.n = 0;
     // lower neighbour sent its c_z = +1 populations (its side-1 message): they go to my ghost plane 0
     const int want = side == 0 ? 1 : -1;
-    const long long gplane = side == 0 ? 0 : G.nzl + 1;
+    const long long gplane = side == 0 ? 0 : G.nzl + 1, bplane = side == 0 ? 1 : G.nzl;
+    int n = 0;
     for (int s = 0; s < 2; ++s)
       for (int i = 0; i < Q; ++i)
-        if (cz(i) == want) {
-          L.src[L.n] = (long long)L.n * G.plane;
-          L.dst[L.n] = (long long)(s * Q + i) * G.comp + gplane * G.plane;
-          ++L.n;
-        }
-    const int T = 256;
-    dim3 grid((unsigned)((G.plane + T - 1) / T), L.n);
-    k_copy_planes<<<grid, T, 0, h->stream>>>(L, recv[side], h->X[h->cur], G.plane);
-    ++h->launches;
-    const long long bplane = side == 0 ? 1 : G.nzl;
-    dim3 gridd((unsigned)((G.plane + T - 1) / T));
-    k_merge_density_halo<<<gridd, T, 0, h->stream>>>(G.plane, (const double2*)(recv[side] + 10 * G.plane),
-                                                     (const double2*)(recv[side] + 12 * G.plane), h->R + bplane * G.plane,
-                                                     h->R + gplane * G.plane);
-    ++h->launches;
+        if (cz(i) == want) U.pop_dst[side][n++] = (long long)(s * Q + i) * G.comp + gplane * G.plane;
+    U.r_bnd[side] = bplane * G.plane;
+    U.r_ghost[side] = gplane * G.plane;
+    if (h->peer_mode) {
+      U.src[side] = mailbox_recv(h->mailbox, h, parity, side);
+      U.flag[side] = mailbox_flag(h->mailbox, h, side);
+    } else {
+      U.src[side] = recv[side];
+      U.flag[side] = nullptr;
+    }
   }
+  U.seq = h->halo_seq;
+  U.err = mailbox_err(h->mailbox, h);
+  const dim3 grid((unsigned)((G.plane + 255) / 256), 11, 2);
+  k_unpack_halo<<<grid, 256, 0, h->stream>>>(U, h->X[h->cur], h->R, G.plane);
+  ++h->launches;
   CU(cudaGetLastError());
   return 0;
 }
@@ -350,6 +381,15 @@ int fold_local(bflbm_lattice* h, int mode, cudaStream_t st = nullptr) {
   else if (mode == 2) k_fold<2><<<grid, block, 0, st>>>(G, h->B, h->E[h->ecur], h->R);
   else if (mode == 3) k_fold<3><<<grid, block, 0, st>>>(G, h->B, h->E[h->ecur], h->R);
   else                k_fold<4><<<grid, block, 0, st>>>(G, h->B, h->E[h->ecur], h->R);
+  ++h->launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+// whole box: brick-face fold + periodic self-exchange (densities and population ghost planes) in one launch;
+// bump > 0 (last step of a graph chunk): advance the device-side step counter
+int fold_wrap_whole_box(bflbm_lattice* h, int bump) {
+  const dim3 grid(h->B.bx, h->B.by, h->B.bz + 1), block(h->B.tx, h->B.ty);
+  k_fold<5><<<grid, block, 0, h->stream>>>(h->G, h->B, h->E[h->ecur], h->R, h->X[h->cur], bump > 0 ? h->d_step : nullptr, bump);
   ++h->launches;
   CU(cudaGetLastError());
   return 0;
@@ -372,10 +412,13 @@ int launch_fused_v(bflbm_lattice* h, int rows, cudaStream_t st) {
   const double2* Ein = (h->e_valid && h->fold_in_staging) ? h->E[h->ecur] : nullptr;
   double2* Eout = h->E[1 - h->ecur];
   const PopBases XB = make_pop_bases(h->G, h->X[h->cur], h->X[1 - h->cur]);
+  // inside a graph capture the step is (device counter) + (offset in the chunk); otherwise it is passed by value
+  const long long step = h->in_graph_capture ? (long long)h->graph_step_off : h->step;
+  const long long* sdev = h->in_graph_capture ? h->d_step : nullptr;
   if (B.tx * B.ty == 128)
-    k_step_fused<NOISE, R1, FU, 128><<<grid, block, fused_smem_bytes(B, R1), st>>>(h->G, B, h->dp, h->step, XB, h->R, Ein, Eout, bz0, two_ends);
+    k_step_fused<NOISE, R1, FU, 128><<<grid, block, fused_smem_bytes(B, R1), st>>>(h->G, B, h->dp, step, sdev, XB, h->R, Ein, Eout, bz0, two_ends);
   else
-    k_step_fused<NOISE, R1, FU, 256><<<grid, block, fused_smem_bytes(B, R1), st>>>(h->G, B, h->dp, h->step, XB, h->R, Ein, Eout, bz0, two_ends);
+    k_step_fused<NOISE, R1, FU, 256><<<grid, block, fused_smem_bytes(B, R1), st>>>(h->G, B, h->dp, step, sdev, XB, h->R, Ein, Eout, bz0, two_ends);
   ++h->launches;
   CU(cudaGetLastError());
   return 0;
@@ -396,14 +439,33 @@ int step_local(bflbm_lattice* h, bool pack = true) {
   // every kernel but the default one stages all planes from R; the default one only when E is not usable
   if ((h->algo != 0 || !h->e_valid || !h->fold_in_staging) && (rc0 = ensure_full_R(h))) return rc0;
   if (h->algo == 1) {
+    // whole box only: z wraps by index arithmetic (Geom::zwrap), so a step is exactly two launches and no ghost plane is
+    // read or written; they are refreshed when the lattice goes back to the fused kernel (bflbm_set_algorithm)
     h->e_valid = false;
-    if (noise) k_step_twopass<true><<<cell_grid(h, h->G.nzl), h->block, 0, h->stream>>>(h->G, h->dp, h->step, h->X[h->cur], h->X[1 - h->cur], h->R);
-    else       k_step_twopass<false><<<cell_grid(h, h->G.nzl), h->block, 0, h->stream>>>(h->G, h->dp, h->step, h->X[h->cur], h->X[1 - h->cur], h->R);
+    const long long step = h->in_graph_capture ? (long long)h->graph_step_off : h->step;
+    const long long* sdev = h->in_graph_capture ? h->d_step : nullptr;
+    const bool rate1 = h->rate1_fast_path && h->dp.rate_f == 1. && h->dp.rate_g == 1.;
+    const dim3 grid = cell_grid(h, h->G.nzl);
+#define BFLBM_TP(N, R1) k_step_twopass<N, R1><<<grid, h->block, 0, h->stream>>>(h->G, h->dp, step, sdev, h->X[h->cur], h->X[1 - h->cur], h->R)
+    if (noise) { if (rate1) BFLBM_TP(true, true); else BFLBM_TP(true, false); }
+    else       { if (rate1) BFLBM_TP(false, true); else BFLBM_TP(false, false); }
+#undef BFLBM_TP
     ++h->launches;
     CU(cudaGetLastError());
     h->cur ^= 1;
+    h->ghosts_stale = true;
     mark(h, 1);
+    k_density<<<cell_grid(h, h->G.nzl), h->block, 0, h->stream>>>(h->G, h->X[h->cur], h->R, h->graph_bump > 0 ? h->d_step : nullptr, h->graph_bump);
+    ++h->launches;
+    CU(cudaGetLastError());
+    mark(h, 2);
+    mark(h, 3);
     return 0;
+  }
+  if (h->ghosts_stale) {  // two-pass steps were taken: the brick kernel reads ghost planes again
+    int rcg;
+    if ((rcg = wrap_population_ghosts(h, h->X[h->cur])) || (rcg = wrap_density_ghosts(h))) return rcg;
+    h->ghosts_stale = false;
   }
   // the default kernel folds the brick-interior planes itself while staging (next step): only the brick faces here
   const bool partial = h->algo == 0 && h->fold_in_staging && fold_in_staging_ok(h->G, h->B);
@@ -439,11 +501,72 @@ int step_local(bflbm_lattice* h, bool pack = true) {
   mark(h, 1);
   h->e_valid = partial;
   h->r_stale = partial;
-  if ((rc = fold_local(h, partial ? 1 : 0))) return rc;
+  // whole box stepped by bflbm_step: the brick-face fold and the periodic self-exchange are one launch
+  h->wrapped_in_fold = h->whole_box && !pack && partial;
+  if ((rc = h->wrapped_in_fold ? fold_wrap_whole_box(h, h->graph_bump) : fold_local(h, partial ? 1 : 0))) return rc;
   mark(h, 2);
   if (pack) rc = pack_halo(h);
   mark(h, 3);
   return rc;
+}
+
+__global__ void k_set_step(long long* p, long long v) { *p = v; }
+
+void drop_graphs(bflbm_lattice* h) {
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  h->graphs.clear();
+}
+bool graph_ok(const bflbm_lattice* h) {
+  if (!h->use_graphs || !h->whole_box || h->profiling) return false;
+  return h->algo == 1 || (h->e_valid && h->fold_in_staging && fold_in_staging_ok(h->G, h->B));
+}
+// K (even) whole-box steps as one graph launch; the graph is captured from the very launches step_local makes
+int run_graph_chunk(bflbm_lattice* h, int K) {
+  const long long key = ((long long)K << 3) | (h->algo << 2) | (h->cur << 1) | h->ecur;
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    const long long launches0 = h->launches;
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->in_graph_capture = true;
+    int rc = 0;
+    for (int j = 0; j < K && !rc; ++j) {
+      h->graph_step_off = j;
+      h->graph_bump = j == K - 1 ? K : 0;
+      rc = step_local(h, /*pack=*/false);
+    }
+    h->in_graph_capture = false;
+    h->graph_bump = 0;
+    h->launches = launches0;
+    const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    if (rc || e != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      h->use_graphs = false;  // e.g. the caller's stream is itself being captured: plain launches from now on
+      return rc ? rc : fail(BFLBM_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
+    }
+    cudaGraphExec_t ex = nullptr;
+    const cudaError_t e2 = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e2 != cudaSuccess) { h->use_graphs = false; return fail(BFLBM_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e2)); }
+    it = h->graphs.emplace(key, ex).first;
+  }
+  if (h->d_step_host != h->step) {
+    k_set_step<<<1, 1, 0, h->stream>>>(h->d_step, h->step);
+    ++h->launches;
+    h->d_step_host = h->step;
+  }
+  CU(cudaGraphLaunch(it->second, h->stream));
+  h->launches += 2 * K;
+  h->step += K;
+  h->d_step_host += K;
+  if (h->algo == 0) {
+    h->e_valid = true;
+    h->r_stale = true;
+  } else {
+    h->ghosts_stale = true;
+  }
+  return 0;
 }
 
 int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, int nzl, int device, bool whole, bflbm_lattice** out) {
@@ -471,6 +594,7 @@ int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, 
   G.nx = nx; G.ny = ny; G.nzl = nzl; G.nz_global = nz_global; G.z0 = z0;
   G.plane = (long long)nx * ny;
   G.comp = (long long)(nzl + 2) * G.plane;
+  G.zwrap = whole ? 1 : 0;
   int bx = 8;
   while (bx < nx && bx < 128) bx <<= 1;
   h->block = dim3(bx, 256 / bx);
@@ -508,9 +632,26 @@ int create_common(const bflbm_params* p, int nx, int ny, int nz_global, int z0, 
     h->fold_in_staging = !(fs && fs[0] == '0');
   }
   h->halo_doubles = (size_t)14 * G.plane;
-  for (int s = 0; s < 2; ++s) {
-    TRY(dev_alloc(h, &h->send[s], h->halo_doubles));
-    if (!whole) TRY(dev_alloc(h, &h->recv[s], h->halo_doubles));
+  for (int s = 0; s < 2; ++s) TRY(dev_alloc(h, &h->send[s], h->halo_doubles));
+  {
+    char* mb = nullptr;
+    TRY(dev_alloc(h, &mb, mailbox_bytes(h)));
+    h->mailbox = reinterpret_cast<double*>(mb);
+    if (cudaMemset(mb, 0, mailbox_bytes(h)) != cudaSuccess) { bflbm_destroy(h); return fail(BFLBM_ERR_CUDA, "cudaMemset(mailbox)"); }
+    for (int s = 0; s < 2; ++s) h->recv[s] = mailbox_recv(h->mailbox, h, 0, s);
+  }
+  {
+    // automatic kernel choice (until the caller asks for an algorithm or a brick height): whole boxes small enough to live in
+    // the 126 MB L2 are latency bound, not bandwidth bound -- the thread-per-cell two-pass kernels (2 launches, no barriers,
+    // no per-CTA prologue) beat the brick sweep there; measured cross-over in profiles/README.md
+    long long small = 150000;
+    if (const char* sc = getenv("BFLBM_SMALL_CELLS")) small = atoll(sc);
+    if (whole && (long long)nx * ny * nzl <= small) h->algo = 1;
+  }
+  TRY(dev_alloc(h, &h->d_step, (size_t)1));
+  {
+    const char* gr = getenv("BFLBM_GRAPH");
+    h->use_graphs = !(gr && gr[0] == '0');
   }
   h->diag_blocks = (size_t)h->grid_xy.x * h->grid_xy.y * nzl;
   TRY(dev_alloc(h, &h->diag_partial, h->diag_blocks * NDIAG));
@@ -546,7 +687,7 @@ int run_init(bflbm_lattice* h, const InitSpec& S) {
 
 // generic chunked observer -> host (or device) array of ncomp components
 template <int MODE>
-int observe(bflbm_lattice* h, int ncomp, double* out, bool out_is_device, bool cell_major) {
+int observe(bflbm_lattice* h, int ncomp, double* out, bool out_is_device, bool cell_major, bool into_global = false) {
   CHECK_H(h);
   if (!out) return fail(BFLBM_ERR_ARG, "null output buffer");
   if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
@@ -564,10 +705,12 @@ int observe(bflbm_lattice* h, int ncomp, double* out, bool out_is_device, bool c
     ++h->launches;
     CU(cudaGetLastError());
     const cudaMemcpyKind kind = out_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    // into_global: `out` is an array of the WHOLE box (component stride nz_global planes); this slab fills its planes
+    const size_t z_off = into_global ? (size_t)G.z0 : 0, comp_planes = into_global ? (size_t)G.nz_global : (size_t)G.nzl;
     if (cell_major) {
-      CU(cudaMemcpyAsync(out + (size_t)zlo * G.plane * ncomp, h->stage, (size_t)zc * G.plane * ncomp * sizeof(double), kind, h->stream));
+      CU(cudaMemcpyAsync(out + ((size_t)zlo + z_off) * G.plane * ncomp, h->stage, (size_t)zc * G.plane * ncomp * sizeof(double), kind, h->stream));
     } else {
-      CU(cudaMemcpy2DAsync(out + (size_t)zlo * G.plane, (size_t)G.nzl * G.plane * sizeof(double), h->stage,
+      CU(cudaMemcpy2DAsync(out + ((size_t)zlo + z_off) * G.plane, comp_planes * G.plane * sizeof(double), h->stage,
                            (size_t)zc * G.plane * sizeof(double), (size_t)zc * G.plane * sizeof(double), ncomp, kind, h->stream));
     }
     // the stage is reused by the next chunk: stream order (kernel after copy) protects it, no host sync per chunk
@@ -576,31 +719,78 @@ int observe(bflbm_lattice* h, int ncomp, double* out, bool out_is_device, bool c
   return 0;
 }
 
-int upload_populations(bflbm_lattice* h, const double* f, const double* g, bool ghosted) {
+// Restart upload.  mode 0: whole box, host arrays (19, nzl, ny, nx).  mode 1: slab, ghosted host arrays (19, nzl+2, ny, nx).
+// mode 2: slab (or whole box), host arrays of the WHOLE box (19, nz_global, ny, nx): the lattice takes its own planes and,
+// for a slab, the two periodic neighbour planes.  Source planes are uploaded in chunks of up to 1 GiB and scattered to
+// their (pre-stream) positions by k_scatter_populations.
+int upload_populations(bflbm_lattice* h, const double* f, const double* g, int mode) {
   const Geom& G = h->G;
   int rc;
-  // host planes are the sources: [0, nzl) of a whole box, [-1, nzl] of a slab (ghosted arrays, host plane index + 1)
-  const int zfirst = ghosted ? -1 : 0, nsrc = ghosted ? G.nzl + 2 : G.nzl;
+  const bool wrap = h->whole_box && mode != 1;  // targets wrap periodically inside the lattice; otherwise ghost planes are sources
+  const int zfirst = wrap ? 0 : -1, nsrc = wrap ? G.nzl : G.nzl + 2;   // source planes zfirst .. zfirst + nsrc - 1 (local numbering)
+  const size_t host_planes = mode == 0 ? (size_t)G.nzl : (mode == 1 ? (size_t)G.nzl + 2 : (size_t)G.nz_global);
   const size_t budget = (size_t)128 << 20;  // doubles (1 GiB): a few large copies per component instead of one per plane
   int cp = (int)std::max<size_t>(1, std::min<size_t>((size_t)nsrc, budget / ((size_t)(2 * Q) * (size_t)G.plane)));
   if ((rc = ensure_stage(h, (size_t)(2 * Q) * cp * G.plane))) return rc;
   const double* src[2] = {f, g};
-  const size_t spitch = (size_t)nsrc * G.plane * sizeof(double);
-  for (int z = 0; z < nsrc; z += cp) {
-    const int zc = std::min(cp, nsrc - z);
+  const size_t spitch = host_planes * G.plane * sizeof(double);
+  // host plane index of local source plane zs
+  auto host_plane = [&](int zs) -> long long {
+    if (mode == 0) return zs;
+    if (mode == 1) return zs + 1;
+    long long zg = (long long)G.z0 + zs;
+    return ((zg % G.nz_global) + G.nz_global) % G.nz_global;
+  };
+  for (int z = 0; z < nsrc;) {
+    int zc = std::min(cp, nsrc - z);
+    if (mode == 2) {  // a chunk must be contiguous in the global array: cut at the periodic wrap
+      const long long hp = host_plane(zfirst + z);
+      zc = (int)std::min<long long>(zc, G.nz_global - hp);
+      if (!wrap && zfirst + z < 0) zc = 1;  // the lower ghost plane is a chunk of its own (its successor may wrap back to plane 0)
+    }
     const size_t dpitch = (size_t)zc * G.plane * sizeof(double);
-    for (int s = 0; s < 2; ++s)
-      CU(cudaMemcpy2DAsync(h->stage + (size_t)s * Q * zc * G.plane, dpitch, src[s] + (size_t)z * G.plane, spitch, dpitch, Q,
+    for (int sp = 0; sp < 2; ++sp)
+      CU(cudaMemcpy2DAsync(h->stage + (size_t)sp * Q * zc * G.plane, dpitch, src[sp] + (size_t)host_plane(zfirst + z) * G.plane, spitch, dpitch, Q,
                            cudaMemcpyHostToDevice, h->stream));
     // stream order protects the stage: the next chunk's copies start after this kernel has read it (no host sync)
-    k_scatter_populations<<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, zfirst + z, ghosted ? 0 : 1, h->stage, h->X[h->cur]);
+    k_scatter_populations<<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, zfirst + z, wrap ? 1 : 0, h->stage, h->X[h->cur]);
     ++h->launches;
     CU(cudaGetLastError());
+    z += zc;
   }
   CU(cudaStreamSynchronize(h->stream));  // the caller's host buffers are free again
   return 0;
 }
 
+// fold/gold or fnoisevs/gnoisevs: one observer pass produces both species (38 components), split into two host arrays
+template <int MODE>
+int observe_pair(bflbm_lattice* h, double* a, double* b, bool into_global) {
+  CHECK_H(h);
+  if (!a || !b) return fail(BFLBM_ERR_ARG, "null output buffer");
+  if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = ensure_full_R(h))) return rc;
+  const Geom& G = h->G;
+  const bool noise = MODE == OBS_NOISE && h->prm.kBT > 0.;
+  const int cp = chunk_planes(h, 2 * Q, 0);
+  if ((rc = ensure_stage(h, (size_t)(2 * Q) * cp * G.plane))) return rc;
+  const size_t z_off = into_global ? (size_t)G.z0 : 0, comp_planes = into_global ? (size_t)G.nz_global : (size_t)G.nzl;
+  for (int zlo = 0; zlo < G.nzl; zlo += cp) {
+    const int zc = std::min(cp, G.nzl - zlo);
+    if (noise) k_observe<MODE, true><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage);
+    else       k_observe<MODE, false><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage);
+    ++h->launches;
+    CU(cudaGetLastError());
+    double* outs[2] = {a, b};
+    for (int s = 0; s < 2; ++s)
+      CU(cudaMemcpy2DAsync(outs[s] + ((size_t)zlo + z_off) * G.plane, comp_planes * G.plane * sizeof(double), h->stage + (size_t)s * Q * zc * G.plane,
+                           (size_t)zc * G.plane * sizeof(double), (size_t)zc * G.plane * sizeof(double), Q, cudaMemcpyDeviceToHost, h->stream));
+    // the stage is reused by the next chunk: stream order (kernel after copy) protects it
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -623,12 +813,16 @@ int bflbm_destroy(bflbm_lattice* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  drop_graphs(h);
+  cudaFree(h->d_step);
   if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
   if (h->ev_prev) cudaEventDestroy(h->ev_prev);
   if (h->ev_ends) cudaEventDestroy(h->ev_ends);
   if (h->ev_interior) cudaEventDestroy(h->ev_interior);
   cudaFree(h->X[0]); cudaFree(h->X[1]); cudaFree(h->R); cudaFree(h->E[0]); cudaFree(h->E[1]);
-  for (int s = 0; s < 2; ++s) { cudaFree(h->send[s]); cudaFree(h->recv[s]); }
+  for (int s = 0; s < 2; ++s) cudaFree(h->send[s]);
+  release_ipc(h);
+  cudaFree(h->mailbox);
   cudaFree(h->stage); cudaFree(h->diag_partial); cudaFree(h->diag_count);
   for (int i = 0; i < 5; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -641,6 +835,7 @@ int bflbm_set_params(bflbm_lattice* h, const bflbm_params* p) {
   int rc = validate_params(p);
   if (rc) return rc;
   const long long keep = h->step;
+  drop_graphs(h);  // the parameters are by-value kernel arguments of the captured launches
   h->prm = *p;
   derive(h);
   h->step = h->initialized ? keep : p->step0;
@@ -657,6 +852,7 @@ int bflbm_set_stream(bflbm_lattice* h, void* s) {
   int rc = set_device(h);
   if (rc) return rc;
   CU(cudaStreamSynchronize(h->stream));
+  drop_graphs(h);
   if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
   if (s) h->stream = (cudaStream_t)s;
   else {
@@ -670,12 +866,17 @@ int bflbm_set_algorithm(bflbm_lattice* h, int algo) {
   if (algo < 0 || algo > 1) return fail(BFLBM_ERR_ARG, "algorithm must be 0 (fused one-pass) or 1 (two-pass)");
   if (algo == 1 && !h->whole_box) return fail(BFLBM_ERR_ARG, "the two-pass algorithm supports whole-box lattices only");
   h->algo = algo;
+  h->algo_auto = false;
   return bflbm_set_tiling(h, h->lz_request);  // the brick shape depends on the kernel
 }
 
 int bflbm_set_tiling(bflbm_lattice* h, int brick_lz) {
   CHECK_H(h);
   if (brick_lz < 0) return fail(BFLBM_ERR_ARG, "brick height must be >= 0");
+  if (brick_lz > 0 && h->algo_auto) {  // a brick height is a request for the brick kernel
+    h->algo_auto = false;
+    h->algo = 0;
+  }
   h->lz_request = brick_lz;
   int rc = set_device(h);
   if (rc) return rc;
@@ -683,6 +884,7 @@ int bflbm_set_tiling(bflbm_lattice* h, int brick_lz) {
   if (h->initialized && (rc = ensure_full_R(h))) return rc;  // E is about to change shape: R takes over
   CU(cudaStreamSynchronize(h->stream));
   h->e_valid = false;
+  drop_graphs(h);
   const BrickGrid nb = make_brick_grid(h->G, brick_lz, h->cta_threads, 32);
   if (brick_doubles2(nb) != brick_doubles2(h->B)) {
     for (int k = 0; k < 2; ++k) {
@@ -717,7 +919,7 @@ int bflbm_init_from_populations(bflbm_lattice* h, const double* f, const double*
   if (!h->whole_box) return fail(BFLBM_ERR_ARG, "slab lattices need bflbm_init_from_populations_slab");
   int rc = set_device(h);
   if (rc) return rc;
-  if ((rc = upload_populations(h, f, g, false))) return rc;
+  if ((rc = upload_populations(h, f, g, 0))) return rc;
   // same partial-sum + self-exchange path a slab takes, so the result does not depend on the slab count
   if ((rc = finish_init(h))) return rc;
   if ((rc = bflbm_halo_refresh_begin(h))) return rc;
@@ -728,13 +930,28 @@ int bflbm_init_from_populations_slab(bflbm_lattice* h, const double* f, const do
   if (!f || !g) return fail(BFLBM_ERR_ARG, "null population buffer");
   int rc = set_device(h);
   if (rc) return rc;
-  if ((rc = upload_populations(h, f, g, true))) return rc;
+  if ((rc = upload_populations(h, f, g, 1))) return rc;
   if ((rc = finish_init(h))) return rc;
   // the ghost planes of X and the densities are completed by bflbm_halo_refresh_begin / exchange / _end,
   // which the caller must run next (done here for a whole box, whose neighbour is itself)
   if (h->whole_box) {
     if ((rc = bflbm_halo_refresh_begin(h))) return rc;
     return bflbm_halo_refresh_end(h);
+  }
+  return 0;
+}
+
+int bflbm_init_from_global_populations(bflbm_lattice* h, const double* f_global, const double* g_global) {
+  CHECK_H(h);
+  if (!f_global || !g_global) return fail(BFLBM_ERR_ARG, "null population buffer");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = upload_populations(h, f_global, g_global, 2))) return rc;
+  if ((rc = finish_init(h))) return rc;
+  // ghost planes of X and the densities: halo refresh (done here when the lattice can do it alone)
+  if (h->whole_box || h->peer_mode) {
+    if ((rc = bflbm_halo_refresh_begin(h))) return rc;
+    if (h->whole_box) return bflbm_halo_refresh_end(h);
   }
   return 0;
 }
@@ -746,15 +963,15 @@ int bflbm_step(bflbm_lattice* h, int nsteps) {
   if (nsteps < 0) return fail(BFLBM_ERR_ARG, "nsteps < 0");
   int rc = set_device(h);
   if (rc) return rc;
-  for (int s = 0; s < nsteps; ++s) {
+  for (int s = 0; s < nsteps;) {
+    if (nsteps - s >= 2 && graph_ok(h)) {
+      int K = 2;
+      for (int c : {64, 16, 4}) if (nsteps - s >= c) { K = c; break; }
+      if ((rc = run_graph_chunk(h, K)) == 0) { s += K; continue; }
+      if (h->use_graphs) return rc;  // a real failure; (capture refused -> use_graphs is off -> plain launches below)
+    }
     if ((rc = step_local(h, /*pack=*/false))) return rc;
-    if (h->algo == 1) {
-      if ((rc = wrap_population_ghosts(h, h->X[h->cur]))) return rc;
-      mark(h, 2);  // two-pass: interval 2 = population ghost wrap, interval 1 -> density pass below
-      if ((rc = density_pass(h))) return rc;
-      mark(h, 3);
-      if ((rc = wrap_density_ghosts(h))) return rc;
-    } else {
+    if (h->algo == 0 && !h->wrapped_in_fold) {
       // periodic self-exchange in one launch (what pack_halo + unpack_halo of my own messages would do)
       k_wrap_whole_box<<<(unsigned)((h->G.plane + 255) / 256), 256, 0, h->stream>>>(h->G, h->X[h->cur], h->R);
       ++h->launches;
@@ -763,12 +980,14 @@ int bflbm_step(bflbm_lattice* h, int nsteps) {
     mark(h, 4);
     profile_collect(h);
     ++h->step;
+    ++s;
   }
   return 0;
 }
 int bflbm_step_begin(bflbm_lattice* h) {
   CHECK_H(h);
   if (!h->initialized) return fail(BFLBM_ERR_STATE, "bflbm_step_begin before init");
+  if (h->algo != 0 && h->algo_auto) h->algo = 0;  // an automatically chosen two-pass whole box asked to step like a slab
   if (h->algo != 0) return fail(BFLBM_ERR_STATE, "slab stepping needs the fused algorithm");
   int rc = set_device(h);
   if (rc) return rc;
@@ -813,6 +1032,108 @@ size_t bflbm_halo_doubles(const bflbm_lattice* h) { return h ? h->halo_doubles :
 void* bflbm_halo_send_buffer(bflbm_lattice* h, int side) { return (h && (side == 0 || side == 1)) ? h->send[side] : nullptr; }
 void* bflbm_halo_recv_buffer(bflbm_lattice* h, int side) { return (h && (side == 0 || side == 1)) ? h->recv[side] : nullptr; }
 
+// ---- peer mode: the halo message goes straight into the neighbour's mailbox over NVLink ---------------------------------
+namespace {
+struct IpcOpen { void* ptr; int refs; };
+std::map<std::string, IpcOpen>& ipc_table() { static std::map<std::string, IpcOpen> t; return t; }
+int peer_connected(bflbm_lattice* h, int side, double* base) {
+  h->peer_base[side] = base;
+  h->peer_mode = h->peer_base[0] != nullptr && h->peer_base[1] != nullptr;
+  return 0;
+}
+}  // namespace
+}  // extern "C"
+void release_ipc(bflbm_lattice* h) {
+  auto& T = ipc_table();
+  for (const std::string& k : h->ipc_keys) {
+    auto it = T.find(k);
+    if (it != T.end() && --it->second.refs == 0) { cudaIpcCloseMemHandle(it->second.ptr); T.erase(it); }
+  }
+  h->ipc_keys.clear();
+}
+extern "C" {
+size_t bflbm_peer_mailbox_bytes(const bflbm_lattice* h) { return h ? mailbox_bytes(h) : 0; }
+void* bflbm_peer_mailbox(bflbm_lattice* h) { return h ? h->mailbox : nullptr; }
+int bflbm_peer_ipc_handle(bflbm_lattice* h, void* out64) {
+  CHECK_H(h);
+  if (!out64) return fail(BFLBM_ERR_ARG, "null output");
+  static_assert(sizeof(cudaIpcMemHandle_t) == BFLBM_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+  int rc = set_device(h);
+  if (rc) return rc;
+  cudaIpcMemHandle_t hd;
+  CU(cudaIpcGetMemHandle(&hd, h->mailbox));
+  memcpy(out64, &hd, sizeof hd);
+  return 0;
+}
+int bflbm_peer_connect(bflbm_lattice* h, int side, void* neighbour_mailbox, int neighbour_device) {
+  CHECK_H(h);
+  if (h->whole_box) return fail(BFLBM_ERR_ARG, "peer mode is for slab lattices");
+  if ((side != 0 && side != 1) || !neighbour_mailbox) return fail(BFLBM_ERR_ARG, "bad side / null mailbox");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (neighbour_device != h->device) {
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, h->device, neighbour_device));
+    if (!can) return fail(BFLBM_ERR_CUDA, "device %d cannot access device %d (no NVLink / PCIe peer path)", h->device, neighbour_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(neighbour_device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(BFLBM_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+  return peer_connected(h, side, static_cast<double*>(neighbour_mailbox));
+}
+int bflbm_peer_connect_ipc(bflbm_lattice* h, int side, const void* handle64) {
+  CHECK_H(h);
+  if (h->whole_box) return fail(BFLBM_ERR_ARG, "peer mode is for slab lattices");
+  if ((side != 0 && side != 1) || !handle64) return fail(BFLBM_ERR_ARG, "bad side / null handle");
+  int rc = set_device(h);
+  if (rc) return rc;
+  // one mapping per (handle, device) and process: with two ranks both neighbours are the same lattice
+  std::string key(static_cast<const char*>(handle64), BFLBM_IPC_HANDLE_BYTES);
+  key += std::to_string(h->device);
+  auto& T = ipc_table();
+  auto it = T.find(key);
+  if (it == T.end()) {
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, sizeof hd);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    it = T.emplace(key, IpcOpen{p, 0}).first;
+  }
+  ++it->second.refs;
+  h->ipc_keys.push_back(key);
+  return peer_connected(h, side, static_cast<double*>(it->second.ptr));
+}
+int bflbm_peer_connected(const bflbm_lattice* h) { return h && h->peer_mode ? 1 : 0; }
+/* begin + exchange + end, nsteps times: in peer mode the exchange IS the pack kernel, so a slab steps like a whole box */
+int bflbm_step_slab(bflbm_lattice* h, int nsteps) {
+  CHECK_H(h);
+  if (!h->peer_mode) return fail(BFLBM_ERR_STATE, "bflbm_step_slab needs both neighbours connected (bflbm_peer_connect / _ipc)");
+  if (nsteps < 0) return fail(BFLBM_ERR_ARG, "nsteps < 0");
+  for (int s = 0; s < nsteps; ++s) {
+    int rc = bflbm_step_begin(h);
+    if (rc == 0) rc = bflbm_step_end(h);
+    if (rc) return rc;
+  }
+  return 0;
+}
+int bflbm_halo_refresh(bflbm_lattice* h) {
+  CHECK_H(h);
+  if (!h->peer_mode && !h->whole_box) return fail(BFLBM_ERR_STATE, "bflbm_halo_refresh needs peer mode (or a whole-box lattice)");
+  int rc = bflbm_halo_refresh_begin(h);
+  return rc ? rc : bflbm_halo_refresh_end(h);
+}
+int bflbm_halo_error(bflbm_lattice* h, int* flag) {
+  CHECK_H(h);
+  int rc = set_device(h);
+  if (rc) return rc;
+  int e = 0;
+  CU(cudaMemcpyAsync(&e, mailbox_err(h->mailbox, h), sizeof e, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (flag) *flag = e;
+  if (e) return fail(BFLBM_ERR_STATE, "a halo wait timed out: the neighbour's message did not arrive within 10 s (rank died or call sequences differ)");
+  return 0;
+}
+
 int bflbm_sync(bflbm_lattice* h) {
   CHECK_H(h);
   int rc = set_device(h);
@@ -831,30 +1152,8 @@ int bflbm_get_dims(const bflbm_lattice* h, int* nx, int* ny, int* nz_local, int*
   return 0;
 }
 
-int bflbm_get_populations(bflbm_lattice* h, double* f, double* g) {
-  CHECK_H(h);
-  if (!f || !g) return fail(BFLBM_ERR_ARG, "null output buffer");
-  // one observer pass produces both species; split into the two host arrays
-  if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
-  int rc = set_device(h);
-  if (rc) return rc;
-  if ((rc = ensure_full_R(h))) return rc;
-  const Geom& G = h->G;
-  const int cp = chunk_planes(h, 2 * Q, 0);
-  if ((rc = ensure_stage(h, (size_t)(2 * Q) * cp * G.plane))) return rc;
-  for (int zlo = 0; zlo < G.nzl; zlo += cp) {
-    const int zc = std::min(cp, G.nzl - zlo);
-    k_observe<OBS_POP, false><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage);
-    ++h->launches;
-    CU(cudaGetLastError());
-    double* outs[2] = {f, g};
-    for (int s = 0; s < 2; ++s)
-      CU(cudaMemcpy2DAsync(outs[s] + (size_t)zlo * G.plane, (size_t)G.nzl * G.plane * sizeof(double), h->stage + (size_t)s * Q * zc * G.plane,
-                           (size_t)zc * G.plane * sizeof(double), (size_t)zc * G.plane * sizeof(double), Q, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-  }
-  return 0;
-}
+int bflbm_get_populations(bflbm_lattice* h, double* f, double* g) { return observe_pair<OBS_POP>(h, f, g, false); }
+int bflbm_get_populations_into_global(bflbm_lattice* h, double* f, double* g) { return observe_pair<OBS_POP>(h, f, g, true); }
 int bflbm_get_populations_device(bflbm_lattice* h, double* dev_f, double* dev_g) {
   CHECK_H(h);
   if (!dev_f || !dev_g) return fail(BFLBM_ERR_ARG, "null output buffer");
@@ -878,22 +1177,14 @@ int bflbm_get_populations_device(bflbm_lattice* h, double* dev_f, double* dev_g)
   }
   return 0;
 }
+int bflbm_get_hydrovars_into_global(bflbm_lattice* h, double* g22) { return observe<OBS_HYDRO>(h, BFLBM_NHYDRO, g22, false, false, true); }
+int bflbm_get_hydrovars_bar_into_global(bflbm_lattice* h, double* g9) { return observe<OBS_HBAR>(h, BFLBM_NHYDRO_BAR, g9, false, false, true); }
 int bflbm_get_hydrovars(bflbm_lattice* h, double* out22) { return observe<OBS_HYDRO>(h, BFLBM_NHYDRO, out22, false, false); }
 int bflbm_get_hydrovars_bar(bflbm_lattice* h, double* out9) { return observe<OBS_HBAR>(h, BFLBM_NHYDRO_BAR, out9, false, false); }
 int bflbm_get_hydrovars_device(bflbm_lattice* h, double* o) { return observe<OBS_HYDRO>(h, BFLBM_NHYDRO, o, true, false); }
 int bflbm_get_hydrovars_bar_device(bflbm_lattice* h, double* o) { return observe<OBS_HBAR>(h, BFLBM_NHYDRO_BAR, o, true, false); }
-int bflbm_get_noise(bflbm_lattice* h, double* fn, double* gn) {
-  CHECK_H(h);
-  if (!fn || !gn) return fail(BFLBM_ERR_ARG, "null output buffer");
-  std::vector<double> tmp;
-  const size_t n = (size_t)h->G.nzl * h->G.plane;
-  try { tmp.resize(2 * Q * n); } catch (...) { return fail(BFLBM_ERR_ARG, "out of host memory"); }
-  int rc = observe<OBS_NOISE>(h, 2 * Q, tmp.data(), false, false);
-  if (rc) return rc;
-  memcpy(fn, tmp.data(), Q * n * sizeof(double));
-  memcpy(gn, tmp.data() + Q * n, Q * n * sizeof(double));
-  return 0;
-}
+int bflbm_get_noise(bflbm_lattice* h, double* fn, double* gn) { return observe_pair<OBS_NOISE>(h, fn, gn, false); }
+int bflbm_get_noise_into_global(bflbm_lattice* h, double* fn, double* gn) { return observe_pair<OBS_NOISE>(h, fn, gn, true); }
 int bflbm_get_normals(bflbm_lattice* h, double* out33) { return observe<OBS_NORMALS>(h, BFLBM_NNORMALS, out33, false, true); }
 
 static int run_diag(bflbm_lattice* h, double sums[NDIAG], unsigned long long* bad) {
@@ -962,18 +1253,24 @@ static void sym3_eigenvalues(const double c[6], double e[3]) {
   e[0] = q + 2. * p * cos(phi + 2. * M_PI / 3.);
   e[1] = 3. * q - e[0] - e[2];
 }
-int bflbm_droplet_covariance(bflbm_lattice* h, double* com3, double* cov6, double* eig3) {
-  CHECK_H(h);
-  if (!h->whole_box) return fail(BFLBM_ERR_ARG, "slab lattice: combine bflbm_second_moments of all slabs instead");
-  double m[10];
-  int rc = bflbm_second_moments(h, m);
-  if (rc) return rc;
+// centre of mass, mass-weighted covariance and its eigenvalues from the ten sums {M, Mx, My, Mz, Mxx, Myy, Mzz, Mxy, Mxz, Myz}
+// (pure host arithmetic: lets the caller combine bflbm_second_moments of several slabs first)
+int bflbm_covariance_from_moments(const double* m, double* com3, double* cov6, double* eig3) {
+  if (!m) return fail(BFLBM_ERR_ARG, "null sums");
   const double M = m[0], cx = m[1] / M, cy = m[2] / M, cz = m[3] / M;
   const double c[6] = {m[4] / M - cx * cx, m[5] / M - cy * cy, m[6] / M - cz * cz, m[7] / M - cx * cy, m[8] / M - cx * cz, m[9] / M - cy * cz};
   if (com3) { com3[0] = cx; com3[1] = cy; com3[2] = cz; }
   if (cov6) for (int k = 0; k < 6; ++k) cov6[k] = c[k];
   if (eig3) sym3_eigenvalues(c, eig3);
   return 0;
+}
+int bflbm_droplet_covariance(bflbm_lattice* h, double* com3, double* cov6, double* eig3) {
+  CHECK_H(h);
+  if (!h->whole_box) return fail(BFLBM_ERR_ARG, "slab lattice: combine bflbm_second_moments of all slabs (bflbm_covariance_from_moments) or use bflbm_multi");
+  double m[10];
+  int rc = bflbm_second_moments(h, m);
+  if (rc) return rc;
+  return bflbm_covariance_from_moments(m, com3, cov6, eig3);
 }
 int bflbm_check_nan(bflbm_lattice* h, long long* count) {
   CHECK_H(h);

@@ -32,16 +32,22 @@
 #define BFLBM_PARK_G 19
 #endif
 #ifndef BFLBM_G_MOMENT_SPACE   // 1: species g keeps its 15 non-conserved MOMENTS in shared memory (30 KB instead of 38 KB per CTA)
-#define BFLBM_G_MOMENT_SPACE 0
+#define BFLBM_G_MOMENT_SPACE 1
 #endif
 #ifndef BFLBM_F_MOMENT_SPACE   // 1: species f is relaxed in moment space in place (full forward transform, no f_old kept)
-#define BFLBM_F_MOMENT_SPACE 0
+#define BFLBM_F_MOMENT_SPACE 1
 #endif
 #ifndef BFLBM_GENERAL_SEQ      // 1: general rates load g, park it, then load f (fewer registers in flight)
-#define BFLBM_GENERAL_SEQ 0
+#define BFLBM_GENERAL_SEQ 1
+#endif
+#ifndef BFLBM_GENERAL_FMA_NOISE  // 1: the general-rate kernels apply the noise in the fma form of the rate-1 kernels
+#define BFLBM_GENERAL_FMA_NOISE 0
+#endif
+#ifndef BFLBM_Y3_LATE            // 1: general rates make the noise key and the momentum normals after the f loads are consumed
+#define BFLBM_Y3_LATE 1
 #endif
 #ifndef BFLBM_F_NORMALS_EARLY
-#define BFLBM_F_NORMALS_EARLY 1
+#define BFLBM_F_NORMALS_EARLY 0
 #endif
 
 namespace bflbm {
@@ -183,9 +189,12 @@ inline PopBases make_pop_bases(const Geom& G, const double* X, double* Xn) {
 // FULL: nx and ny are multiples of the tile, every thread owns a cell (no activity predicates, no divergence code).
 template <bool NOISE, bool RATE1, bool FULL, int NT>
 __global__ void __launch_bounds__(NT, 512 / NT)
-k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B, const __grid_constant__ DevParams P, long long step,
-             const __grid_constant__ PopBases XB, const double2* __restrict__ R, const double2* __restrict__ Ein,
-             double2* __restrict__ E, int bz0, int two_ends) {
+k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B, const __grid_constant__ DevParams P, long long step_arg,
+             const long long* __restrict__ step_dev, const __grid_constant__ PopBases XB, const double2* __restrict__ R,
+             const double2* __restrict__ Ein, double2* __restrict__ E, int bz0, int two_ends) {
+  // time step of the noise key: by value, plus (launches replayed from a CUDA graph) a counter in device memory that the
+  // last kernel of every replayed chunk advances -- the arguments of a captured launch cannot change between replays
+  const long long step = step_arg + ((NOISE && step_dev != nullptr) ? *step_dev : 0ll);
   // brick row of this CTA: rows bz0 .. bz0+gridDim.z-1, or (two_ends) the first and the last row of the slab -- the
   // rows whose results the halo message needs, launched first so that the exchange overlaps the interior rows
   const int bZ = two_ends ? (blockIdx.z == 0 ? 0 : B.bz - 1) : bz0 + (int)blockIdx.z;
@@ -197,6 +206,7 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
   double* So = reinterpret_cast<double*>(Fix + FIX_SLOTS);  // [19][NT] incoming populations of species g (!RATE1)
   // rate-1 kernels make all 33 normals in the load shadow; the general kernels (19 more live doubles) make g's 15 late
   constexpr int PARK_F = BFLBM_PARK_F, PARK_G = BFLBM_PARK_G;
+  constexpr bool FMA_NOISE = RATE1 || BFLBM_GENERAL_FMA_NOISE;  // how the noise is applied (philox.cuh)
   constexpr bool G_NORMALS_EARLY = RATE1 || BFLBM_G_NORMALS_EARLY, F_NORMALS_EARLY = RATE1 || BFLBM_F_NORMALS_EARLY;
   __shared__ int nfix;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * B.tx + tx;
@@ -344,7 +354,7 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
     {
       double mf[Q], mg[Q];
       double fo[Q];  // incoming populations of species f: weight (1 - w_f) in the result (general rates only)
-      double gk[(BFLBM_G_MOMENT_SPACE ? 4 : Q - PARK_G) + 1];  // ... and the few of species g that do not wait in shared memory
+      double gk[(BFLBM_G_MOMENT_SPACE ? 0 : Q - PARK_G) + 1];  // ... and the few of species g that do not wait in shared memory
       float ybg[15];
       unsigned c = 0;  // byte offset of this cell inside a component
       CollideCtx C;
@@ -391,8 +401,11 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
 #pragma unroll
             for (int i = 0; i < Q; ++i) fo[i] = ld_off(XB.in[i], off[i]);
           }
-          nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
-          momentum_normals<NOISE>(nk, y3);
+          constexpr bool Y3_LATE = !RATE1 && BFLBM_Y3_LATE;
+          if (!Y3_LATE) {
+            nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
+            momentum_normals<NOISE>(nk, y3);
+          }
           if (F_NORMALS_EARLY) mode_normals<NOISE, 0>(nk, ybf);
           if (G_NORMALS_EARLY) mode_normals<NOISE, 1>(nk, ybg);
           // only the conserved moments (density, momentum) of the incoming state are needed (physics.cuh, collide_species):
@@ -402,8 +415,6 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
             if (BFLBM_G_MOMENT_SPACE) {
 #pragma unroll
               for (int a = 4; a < Q; ++a) So[(a - 4) * NT + tid] = mg[a];
-#pragma unroll
-              for (int a = 0; a < 4; ++a) gk[a] = mg[a];
             } else {
 #pragma unroll
               for (int i = 0; i < PARK_G; ++i) So[i * NT + tid] = go[i];
@@ -416,14 +427,18 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
             for (int i = 0; i < Q; ++i) fo[i] = ld_off(XB.in[i], off[i]);
           }
           moments(fo, mf);
+          if (Y3_LATE) {
+            nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
+            momentum_normals<NOISE>(nk, y3);
+          }
           if (!RATE1) {  // ... and so do the first PARK_F incoming populations of f (register pressure at the inverse transform)
 #pragma unroll
             for (int i = 0; i < PARK_F; ++i) So[(PARK_G + i) * NT + tid] = fo[i];
           }
         }
-        collide_prepare<NOISE>(P, grho, gphi, y3, mf, mg, C);
+        collide_prepare<NOISE, FMA_NOISE>(P, grho, gphi, y3, mf, mg, C);
         if (!F_NORMALS_EARLY) mode_normals<NOISE, 0>(nk, ybf);
-        collide_species<NOISE, 0, RATE1, !RATE1 && BFLBM_F_MOMENT_SPACE>(P, ybf, C, mf);
+        collide_species<NOISE, 0, RATE1, !RATE1 && BFLBM_F_MOMENT_SPACE, FMA_NOISE>(P, ybf, C, mf);
       } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) mf[i] = fo[i] = 0.;
@@ -444,18 +459,15 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
       ef[0] = left ? p[2] : p[1]; ef[1] = left ? p[10] : p[7]; ef[2] = left ? p[8] : p[9];
       ef[3] = left ? p[18] : p[15]; ef[4] = left ? p[16] : p[17];
       if (active) {
+        if (!RATE1 && BFLBM_G_MOMENT_SPACE) {  // moment space, in place: m <- (1 - w) m_old + v, then one inverse transform
+#pragma unroll
+          for (int a = 4; a < Q; ++a) mg[a] = So[(a - 4) * NT + tid];
+        }
         if (!G_NORMALS_EARLY) mode_normals<NOISE, 1>(nk, ybg);
-        collide_species<NOISE, 1, RATE1>(P, ybg, C, mg);
+        collide_species<NOISE, 1, RATE1, !RATE1 && BFLBM_G_MOMENT_SPACE, FMA_NOISE>(P, ybg, C, mg);
       } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) mg[i] = 0.;
-      }
-      if (!RATE1 && BFLBM_G_MOMENT_SPACE && active) {  // moment space: m <- (1 - w) m_old + v, then one inverse transform
-        const double kg = keep_of(P, 1);
-#pragma unroll
-        for (int a = 0; a < 4; ++a) mg[a] = fma(kg, gk[a], mg[a]);
-#pragma unroll
-        for (int a = 4; a < Q; ++a) mg[a] = fma(kg, So[(a - 4) * NT + tid], mg[a]);
       }
       populations(mg, p);
       if (!RATE1 && !BFLBM_G_MOMENT_SPACE && active) {
@@ -532,12 +544,32 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
 // MODE 3 + MODE 4 = MODE 1 split for the overlapped slab step: 3 = the four planes at the slab faces (zl = -1, 0,
 // nzl-1, nzl: all the halo message needs, computable from the first and last brick row alone; launched with two
 // z-blocks), 4 = the remaining brick-face planes.
+// MODE 5 = MODE 1 for a WHOLE-BOX lattice, with the periodic self-exchange folded in (the lattice is its own z-neighbour):
+// the thread that sums plane 0 also sums this lattice's contribution to "the upper neighbour's" boundary plane and stores
+// boundary = local + remote, ghost = remote + local (the operand order of k_merge_density_halo, hence bit-identical to any slab
+// decomposition); likewise at the top.  One extra z-layer of CTAs copies the 5+5 population planes that stream across the
+// periodic face into the ghost planes, and its first thread advances the device-side step counter (CUDA-graph replays).
+// A whole-box step is then TWO launches (k_step_fused, k_fold<5>); it was 10, then 3, in round 1.
 template <int MODE>
-__global__ void __launch_bounds__(256, 4) k_fold(Geom G, BrickGrid B, const double2* __restrict__ E, double2* __restrict__ R) {
+__global__ void __launch_bounds__(256, 4) k_fold(Geom G, BrickGrid B, const double2* __restrict__ E, double2* __restrict__ R,
+                                                  double* X = nullptr, long long* step_dev = nullptr, int step_bump = 0) {
   const int bX = blockIdx.x, bY = blockIdx.y, bZ = MODE == 3 ? (blockIdx.z == 0 ? 0 : B.bz - 1) : (int)blockIdx.z;
   const int lx = threadIdx.x, ly = threadIdx.y;
   const int x = bX * B.tx + lx, y = bY * B.ty + ly;
+  if (MODE == 5 && step_dev != nullptr && (blockIdx.x | blockIdx.y) == 0 && blockIdx.z == B.bz && (lx | ly) == 0) *step_dev += step_bump;
   if (x >= G.nx || y >= G.ny) return;
+  if (MODE == 5 && bZ == B.bz) {  // ghost planes of the populations that cross the periodic face
+    const long long i = (long long)y * G.nx + x, top = (long long)G.nzl * G.plane;
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        double* Xc = X + (long long)(s * Q + q) * G.comp + i;
+        if (cz(q) == 1) Xc[0] = Xc[top];                  // pulled from the plane below: ghost plane 0 <- plane nzl-1
+        if (cz(q) == -1) Xc[top + G.plane] = Xc[G.plane];  // ghost plane nzl <- plane 0
+      }
+    return;
+  }
   int inpl[3][3];
   fold_candidates(G, B, x, y, inpl);
   const long long zrow = (long long)B.by * B.bx * B.brick;  // E stride between brick rows in z
@@ -560,12 +592,12 @@ __global__ void __launch_bounds__(256, 4) k_fold(Geom G, BrickGrid B, const doub
   };
   const int zb = bZ * B.lz, vz = min(B.lz, G.nzl - zb);
   double2* Rc = R + (long long)y * G.nx + x;
-  if (MODE != 2 && MODE != 4) {
+  if (MODE != 2 && MODE != 4 && MODE != 5) {
     // with one brick row, MODE 3 runs a single z-block that owns both faces
     if (bZ == 0 && (MODE != 3 || blockIdx.z == 0)) Rc[0] = group(0, 0);  // zl = -1 : my share of the lower neighbour's boundary plane
     if (bZ == B.bz - 1 && (MODE != 3 || blockIdx.z == gridDim.z - 1)) Rc[(long long)(G.nzl + 1) * G.plane] = group(bZ, vz + 1);  // zl = nzl
   }
-  auto plane = [&](int l) {
+  auto plane_value = [&](int l) {
     double2 tot = group(bZ, l + 1);
     if (l == 0 && bZ > 0) {  // a lower brick is always full height
       const double2 s = group(bZ - 1, B.lz + 1);
@@ -577,9 +609,31 @@ __global__ void __launch_bounds__(256, 4) k_fold(Geom G, BrickGrid B, const doub
       tot.x += s.x;
       tot.y += s.y;
     }
-    Rc[(long long)(zb + l + 1) * G.plane] = tot;
+    return tot;
   };
-  if (MODE == 1) {
+  auto plane = [&](int l) { Rc[(long long)(zb + l + 1) * G.plane] = plane_value(l); };
+  if (MODE == 5) {
+    const bool first = bZ == 0, last = bZ == B.bz - 1;
+    const double2 v0 = plane_value(0);
+    const double2 v1 = vz > 1 ? plane_value(vz - 1) : v0;
+    if (first) {  // r1 + rn1: plane 0 and the ghost plane above the top
+      const int vzl = G.nzl - (B.bz - 1) * B.lz;
+      const double2 e = group(B.bz - 1, vzl + 1);
+      const double2 m = make_double2(v0.x + e.x, v0.y + e.y);
+      Rc[G.plane] = m;
+      Rc[(long long)(G.nzl + 1) * G.plane] = m;
+    } else if (!(last && vz == 1)) {
+      Rc[(long long)(zb + 1) * G.plane] = v0;
+    }
+    if (last) {   // rn + r0: the top plane and the ghost plane below plane 0
+      const double2 e = group(0, 0);
+      const double2 m = make_double2(v1.x + e.x, v1.y + e.y);
+      Rc[(long long)G.nzl * G.plane] = m;
+      Rc[0] = m;
+    } else if (vz > 1) {
+      Rc[(long long)(zb + vz) * G.plane] = v1;
+    }
+  } else if (MODE == 1) {
     plane(0);
     if (vz > 1) plane(vz - 1);
   } else if (MODE == 3) {  // slab faces: plane 0 of the first row, the last plane of the last row
@@ -639,6 +693,95 @@ __global__ void __launch_bounds__(256) k_wrap_whole_box(Geom G, double* X, doubl
   R[i] = make_double2(rn.x + r0.x, rn.y + r0.y);
   R[top + i] = make_double2(rn.x + r0.x, rn.y + r0.y);
   R[top + G.plane + i] = make_double2(r1.x + rn1.x, r1.y + rn1.y);
+}
+
+// ---- halo messages of a slab: ONE pack launch, ONE unpack launch, optionally straight into the neighbour's memory ----------
+// message to the neighbour on `side` (0: lower z, 1: upper z), 14 * plane doubles:
+//   [10][plane]   the 5+5 populations of my boundary plane that the neighbour pulls across the face
+//   [2 * plane]   Pz: my local partial (rho, phi) sums on my boundary plane
+//   [2 * plane]   Ez: my contribution to (rho, phi) on the neighbour's boundary plane
+// dst[side] is either this lattice's own send buffer (the caller moves it: NCCL / copies) or -- peer mode -- the receive
+// slot inside the NEIGHBOUR's mailbox, mapped into this GPU's address space (same process: peer access; other process:
+// CUDA IPC): the pack kernel's stores ARE the transfer over NVLink, no copy kernel, no NCCL kernel, nothing to wait for on
+// the host.  Arrival is signalled through a sequence number: every thread fences its stores system-wide, the last CTA of
+// the grid (atomic counter) then writes `seq` to the neighbour's flag.
+struct HaloPack {
+  long long pop_src[2][10];        // offsets (doubles) into X of the 10 components' boundary planes, per side
+  long long r_bnd[2], r_out[2];    // offsets (doubles) into R of my boundary plane / the plane just outside the slab
+  double* dst[2];
+  unsigned long long* flag[2];     // peer mode: the neighbour's arrival flag for this message; otherwise null
+  unsigned long long seq;
+  unsigned int* done;              // CTA counter of this lattice (peer mode)
+};
+__global__ void __launch_bounds__(256) k_pack_halo(const __grid_constant__ HaloPack H, const double* __restrict__ X,
+                                                    const double* __restrict__ R, long long plane) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, side = blockIdx.z;
+  if (i < plane) {
+    double v;
+    if (j < 10) v = X[H.pop_src[side][j] + i];
+    else if (j < 12) v = R[H.r_bnd[side] + (long long)(j - 10) * plane + i];
+    else v = R[H.r_out[side] + (long long)(j - 12) * plane + i];
+    H.dst[side][(long long)j * plane + i] = v;
+  }
+  if (H.flag[0] != nullptr) {
+    __threadfence_system();  // my store is visible system-wide before anything I (or a thread that observes me) do next
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+      if (atomicAdd(H.done, 1u) == total - 1) {
+        *H.done = 0;  // next launch on this stream starts from zero
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(H.flag[0]), "l"(H.seq) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(H.flag[1]), "l"(H.seq) : "memory");
+      }
+    }
+  }
+}
+
+// src[side]: the message that arrived from the neighbour on `side`.  Peer mode: flag[side] is MY arrival flag for it; every CTA
+// waits until it shows `seq` (acquire), bounded by a 10 s timeout that sets *err instead of hanging the GPU.
+//   j < 10 : ghost plane of one population component      j == 10 : the density merge
+//   boundary plane:  R <- local + Ez(neighbour's contribution)      ghost plane:  R <- Pz(neighbour's local) + mine
+struct HaloUnpack {
+  long long pop_dst[2][10];
+  long long r_bnd[2], r_ghost[2];  // offsets in double2 units into R
+  const double* src[2];
+  const unsigned long long* flag[2];
+  unsigned long long seq;
+  int* err;
+};
+__global__ void __launch_bounds__(256) k_unpack_halo(const __grid_constant__ HaloUnpack U, double* __restrict__ X, double2* __restrict__ R,
+                                                      long long plane) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, side = blockIdx.z;
+  if (U.flag[side] != nullptr) {
+    if (threadIdx.x == 0) {
+      unsigned long long t0 = 0, now, seen;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(U.flag[side]) : "memory");
+        if (seen >= U.seq) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 10000000000ull) { atomicExch(U.err, 1); break; }
+        __nanosleep(200);
+      }
+    }
+    __syncthreads();
+  }
+  if (i >= plane) return;
+  const double* m = U.src[side];
+  if (j < 10) {
+    X[U.pop_dst[side][j] + i] = __ldcg(m + (long long)j * plane + i);
+  } else {
+    const double2 p = __ldcg(reinterpret_cast<const double2*>(m + 10 * plane) + i);
+    const double2 e = __ldcg(reinterpret_cast<const double2*>(m + 12 * plane) + i);
+    double2 b = R[U.r_bnd[side] + i], g = R[U.r_ghost[side] + i];
+    b.x += e.x; b.y += e.y;
+    g.x = p.x + g.x; g.y = p.y + g.y;
+    R[U.r_bnd[side] + i] = b;
+    R[U.r_ghost[side] + i] = g;
+  }
 }
 
 // receiving side of the density part of a halo message:

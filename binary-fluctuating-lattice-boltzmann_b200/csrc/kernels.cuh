@@ -15,6 +15,7 @@ namespace bflbm {
 struct Geom {
   int nx, ny, nzl;      // local slab (valid cells)
   int nz_global, z0;    // global box height and first global plane of the slab
+  int zwrap;            // 1: whole box -- the thread-per-cell kernels wrap z by index arithmetic and never read a ghost plane
   long long plane;      // nx*ny
   long long comp;       // (nzl+2)*plane  : stride between components of X
 };
@@ -37,9 +38,9 @@ __device__ __forceinline__ CellIdx cell_idx(const Geom& G, int x, int y, int zl)
   I.yrow[0] = (long long)((y == 0) ? G.ny - 1 : y - 1) * G.nx;
   I.yrow[1] = (long long)y * G.nx;
   I.yrow[2] = (long long)((y == G.ny - 1) ? 0 : y + 1) * G.nx;
-  I.zpl[0] = (long long)zl * G.plane;
+  I.zpl[0] = (long long)((G.zwrap && zl == 0) ? G.nzl : zl) * G.plane;
   I.zpl[1] = (long long)(zl + 1) * G.plane;
-  I.zpl[2] = (long long)(zl + 2) * G.plane;
+  I.zpl[2] = (long long)((G.zwrap && zl == G.nzl - 1) ? 1 : zl + 2) * G.plane;
   return I;
 }
 // index of the cell at (x,y,z) + s*c_i, s = +1 or -1
@@ -57,8 +58,11 @@ __device__ __forceinline__ void pull19(const double* __restrict__ Xs, const Geom
 // ---------------------------------------------------------------------------------------------
 // two-pass algorithm, pass 1: (rho, phi) of the post-stream populations
 // (LBM_hydrovars_density, LBM_binary.H:343-354: sequential sum i = 0..18)
-__global__ void __launch_bounds__(256) k_density(Geom G, const double* __restrict__ X, double2* __restrict__ R) {
+// step_dev / bump: last launch of a CUDA-graph chunk advances the device-side step counter (see k_step_fused)
+__global__ void __launch_bounds__(256) k_density(Geom G, const double* __restrict__ X, double2* __restrict__ R,
+                                                  long long* step_dev = nullptr, int bump = 0) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zl = blockIdx.z;
+  if (step_dev != nullptr && (x | y | zl) == 0) *step_dev += bump;
   if (x >= G.nx || y >= G.ny) return;
   const CellIdx I = cell_idx(G, x, y, zl);
   double f[Q], g[Q];
@@ -87,11 +91,14 @@ __device__ __forceinline__ void density_gradients(const double2* __restrict__ R,
 // two-pass algorithm, pass 2: pull-stream + hydro + collide (+noise) + store.
 // Covers K1 (collide_stream, LBM_binary.H:565-573), K4 (thermal_noise :91-128) and K5 (hydrovars :309-311)
 // of SURVEY.md 2b in one kernel; the reference's two Swaps (:579-580) become a pointer swap on the host.
-template <bool NOISE>
-__global__ void __launch_bounds__(256) k_step_twopass(Geom G, DevParams P, long long step, const double* __restrict__ X,
-                                                       double* __restrict__ Xn, const double2* __restrict__ R) {
+// RATE1 (tau_f = tau_g = 1/2): the old populations do not enter the result, the 76 registers that hold them are free after
+// the conserved moments are formed.  Two CTAs per SM (<= 128 registers): these kernels serve the small, latency-bound boxes.
+template <bool NOISE, bool RATE1>
+__global__ void __launch_bounds__(256, RATE1 ? 2 : 1) k_step_twopass(Geom G, DevParams P, long long step_arg, const long long* __restrict__ step_dev,
+                                                       const double* __restrict__ X, double* __restrict__ Xn, const double2* __restrict__ R) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zl = blockIdx.z;
   if (x >= G.nx || y >= G.ny) return;
+  const long long step = step_arg + ((NOISE && step_dev != nullptr) ? *step_dev : 0ll);
   const CellIdx I = cell_idx(G, x, y, zl);
   double f[Q], g[Q], mf[Q], mg[Q];
   pull19(X, G, I, f);
@@ -108,16 +115,16 @@ __global__ void __launch_bounds__(256) k_step_twopass(Geom G, DevParams P, long 
   const long long c = I.zpl[1] + I.yrow[1] + x;
   double p[Q];
   mode_normals<NOISE, 0>(nk, yb);
-  collide_species<NOISE, 0, false>(P, yb, C, mf);
+  collide_species<NOISE, 0, RATE1>(P, yb, C, mf);
   populations(mf, p);
   const double kf = keep_of(P, 0), kg = keep_of(P, 1);
 #pragma unroll
-  for (int i = 0; i < Q; ++i) Xn[(long long)i * G.comp + c] = fma(kf, f[i], p[i]);
+  for (int i = 0; i < Q; ++i) Xn[(long long)i * G.comp + c] = RATE1 ? p[i] : fma(kf, f[i], p[i]);
   mode_normals<NOISE, 1>(nk, yb);
-  collide_species<NOISE, 1, false>(P, yb, C, mg);
+  collide_species<NOISE, 1, RATE1>(P, yb, C, mg);
   populations(mg, p);
 #pragma unroll
-  for (int i = 0; i < Q; ++i) Xn[(long long)(Q + i) * G.comp + c] = fma(kg, g[i], p[i]);
+  for (int i = 0; i < Q; ++i) Xn[(long long)(Q + i) * G.comp + c] = RATE1 ? p[i] : fma(kg, g[i], p[i]);
 }
 
 // ---------------------------------------------------------------------------------------------

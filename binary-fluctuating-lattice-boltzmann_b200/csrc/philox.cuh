@@ -76,6 +76,16 @@ __device__ __forceinline__ double widen_pos(float y) {  // exact for every posit
   const unsigned u = __float_as_uint(y);
   return __hiloint2double((int)((u >> 3) + 0x38000000u), (int)(u << 29));
 }
+// General float -> double re-packing (sign handled: 5 integer operations), exact for every normal float, and the normal
+// as an fp32 number: n = 16 y - 24 is exact in fp32 (y and 1.5 share their exponent).  The general-rate kernels, which are
+// short of registers, apply the noise as  m += amplitude * widen(n)  (round 1's form, 18.1 ms against 19.2+ ms for the fma
+// form at 512^3, profiles/README.md); both forms see the same normals.
+__device__ __forceinline__ double widen(float f) {
+  const unsigned u = __float_as_uint(f);
+  const unsigned hi = (((u & 0x7fffffffu) >> 3) + 0x38000000u) | (u & 0x80000000u);
+  return __hiloint2double((int)hi, (int)(u << 29));
+}
+__device__ __forceinline__ float normal_f32(float y) { return fmaf(y, 16.f, -24.f); }
 // the standard normal itself (observers, tests): exact, y has 24 significant bits
 __device__ __forceinline__ double normal_of(float y) { return NRM_SCALE * (widen_pos(y) - NRM_BIAS); }
 

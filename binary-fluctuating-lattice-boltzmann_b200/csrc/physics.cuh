@@ -57,7 +57,7 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
 // when !NOISE.  sq_rho / sq_phi return sqrt|rho|, sqrt|phi| (for the stress-mode noise amplitudes of collide_species).
 // The three reciprocals (1/rho, 1/phi, 1/(rho+phi)) and three square roots the formulas need all come from three
 // reciprocal square roots: 1/x = sign(x) r^2, sqrt|x| = |x| r with r = rsqrt|x|  (each ~2 ulp; the bar is 1e-12).
-template <bool NOISE>
+template <bool NOISE, bool FMA_NOISE = true>
 __device__ __forceinline__ void cell_hydro(const DevParams& P, double rho, double phi, const double (&jf)[3], const double (&jg)[3],
                                            const double (&grad_rho)[3], const double (&grad_phi)[3], const float (&y3)[3],
                                            CellHydro& H, double& sq_rho, double& sq_phi) {
@@ -89,7 +89,7 @@ __device__ __forceinline__ void cell_hydro(const DevParams& P, double rho, doubl
     H.ugb[k] = jg[k] * inv_phi;
     H.af[k] = has_f ? P.acc_coef * grad_phi[k] : 0.;
     H.ag[k] = has_g ? P.acc_coef * grad_rho[k] : 0.;
-    H.xi[k] = NOISE ? fma(amp16, widen_pos(y3[k]), ampb) : 0.;
+    H.xi[k] = NOISE ? (FMA_NOISE ? fma(amp16, widen_pos(y3[k]), ampb) : (amp16 * (1. / NRM_SCALE)) * widen(normal_f32(y3[k]))) : 0.;
     H.nfv[k] = H.xi[k] * inv_rho;
     H.ngv[k] = -H.xi[k] * inv_phi;
     const double d = (H.ufb[k] - H.ugb[k]) + 0.5 * (H.af[k] - H.ag[k]);
@@ -120,11 +120,11 @@ struct CollideCtx {
 // The standard normals come from the caller (momentum_normals / mode_normals below) in biased form: y3 = the three
 // momentum-mode draws, yb = the 15 draws of modes 4..18 of the species.  Generating them is pure arithmetic on the cell's
 // counter, so the step kernel does it in the shadow of its population loads, before the first loaded value is needed.
-template <bool NOISE>
+template <bool NOISE, bool FMA_NOISE = true>
 __device__ __forceinline__ void collide_prepare(const DevParams& P, const double (&grad_rho)[3], const double (&grad_phi)[3],
                                                 const float (&y3)[3], const double (&mf)[Q], const double (&mg)[Q], CollideCtx& C) {
   const double jf[3] = {mf[1], mf[2], mf[3]}, jg[3] = {mg[1], mg[2], mg[3]};
-  cell_hydro<NOISE>(P, mf[0], mg[0], jf, jg, grad_rho, grad_phi, y3, C.H, C.sq_rho, C.sq_phi);
+  cell_hydro<NOISE, FMA_NOISE>(P, mf[0], mg[0], jf, jg, grad_rho, grad_phi, y3, C.H, C.sq_rho, C.sq_phi);
 #pragma unroll
   for (int k = 0; k < 3; ++k) C.vb[k] = (C.H.rho * C.H.uf[k] + C.H.phi * C.H.ug[k]) * C.H.inv_tot;  // LBM_binary.H:471
 }
@@ -133,7 +133,8 @@ __device__ __forceinline__ void collide_prepare(const DevParams& P, const double
 // forcing :404-449, noise :113-127).  rate = w; RATE1: w is exactly 1 (saves the multiplications by it).
 // INPLACE: v holds ALL 19 incoming moments and is relaxed in place, v_k <- (1 - w) v_k + (w meq + Phi + noise)_k -- the
 // moment-space form of the same update (one array instead of two: used where registers are short).
-template <bool NOISE, int SPECIES, bool RATE1, bool INPLACE = false>
+// FMA_NOISE = false: the noise of modes 4..18 is added afterwards as  v_k += amplitude_k * widen(n_k)  (see philox.cuh).
+template <bool NOISE, int SPECIES, bool RATE1, bool INPLACE = false, bool FMA_NOISE = true>
 __device__ __forceinline__ void collide_species(const DevParams& P, const float (&yb)[15], const CollideCtx& C, double (&v)[Q]) {
   const CellHydro& H = C.H;
   const double D = SPECIES == 0 ? H.rho : H.phi, rate = SPECIES == 0 ? P.rate_f : P.rate_g;
@@ -146,7 +147,7 @@ __device__ __forceinline__ void collide_species(const DevParams& P, const float 
   const double keep = 1. - rate;
   auto old = [&](int k, double x) { return INPLACE ? fma(keep, v[k], x) : x; };
   auto set = [&](int k, double eq, double force) {  // v_k = Dr eq + Dp force + noise_k
-    if (NOISE) {
+    if (NOISE && FMA_NOISE) {
       const double amp = sqrt_bnorm(k) * s16;
       v[k] = fma(amp, widen_pos(yb[k - 4]), fma(Dr, eq, fma(Dp, force, old(k, -NRM_BIAS * amp))));
     } else {
@@ -168,12 +169,17 @@ __device__ __forceinline__ void collide_species(const DevParams& P, const float 
   // ghost modes: no equilibrium, no force
 #pragma unroll
   for (int k = 10; k < Q; ++k) {
-    if (NOISE) {
+    if (NOISE && FMA_NOISE) {
       const double amp = sqrt_bnorm(k) * s16;
       v[k] = fma(amp, widen_pos(yb[k - 4]), old(k, -NRM_BIAS * amp));
     } else {
       v[k] = INPLACE ? keep * v[k] : 0.;
     }
+  }
+  if (NOISE && !FMA_NOISE) {
+    const double s = s16 * (1. / NRM_SCALE);  // sqrt(A kBT/cs2 |D|), LBM_binary.H:125-126
+#pragma unroll
+    for (int k = 4; k < Q; ++k) v[k] += (sqrt_bnorm(k) * s) * widen(normal_f32(yb[k - 4]));
   }
 }
 // (1 - w) of the species: the weight of the old populations in the post-collision state

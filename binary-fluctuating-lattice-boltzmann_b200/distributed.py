@@ -54,6 +54,19 @@ def exchange_ring(send_lo, send_hi, recv_lo, recv_hi, rank: int, world: int, gro
         req.wait()
 
 
+def gather_ring_handles(handle: bytes, rank: int, world: int, group=None) -> tuple[bytes, bytes]:
+    """Peer mode plumbing: every rank publishes the 64-byte CUDA-IPC handle of its mailbox (bflbm_peer_ipc_handle); returns the
+    handles of (lower neighbour, upper neighbour) on the periodic ring.  The only collective of the peer path, once per run."""
+    import torch.distributed as dist
+    handles = [None] * world
+    if world == 1:
+        handles[0] = handle
+    else:
+        dist.all_gather_object(handles, handle, group=group)
+    lo, hi = neighbours(world, rank)
+    return handles[lo], handles[hi]
+
+
 def _device_tensor(ptr: int, n: int, device):
     """float64 torch view of `n` doubles of device memory owned by the C library."""
     import torch
@@ -71,9 +84,10 @@ class EmulatedSlabs:
     place of the NCCL messages.  Exercises exactly the library path a multi-GPU run takes (bflbm_create_slab,
     step_begin / step_end, halo buffers); used by the single-GPU tests of the slab logic."""
 
-    def __init__(self, nx, ny, nz, nslabs, params: Params | None = None, device: int = 0, brick_lz: int = 0):
+    def __init__(self, nx, ny, nz, nslabs, params: Params | None = None, device: int = 0, brick_lz: int = 0, peer: bool = False):
         import torch
         self.world, self.nz_global = nslabs, nz
+        self.peer = peer
         self.device = torch.device("cuda", device)
         self.stream = torch.cuda.Stream(device=self.device)
         self.bounds = [slab_bounds(nz, nslabs, r) for r in range(nslabs)]
@@ -86,6 +100,11 @@ class EmulatedSlabs:
         lib = self.lats[0].lib
         self.send = [[_device_tensor(lib.bflbm_halo_send_buffer(l.h, s), n, self.device) for s in (0, 1)] for l in self.lats]
         self.recv = [[_device_tensor(lib.bflbm_halo_recv_buffer(l.h, s), n, self.device) for s in (0, 1)] for l in self.lats]
+        if peer:  # peer mode on one device: the "neighbour's mailbox" is ordinary device memory of the same GPU
+            for r, lat in enumerate(self.lats):
+                lo, hi = neighbours(self.world, r)
+                lat.peer_connect(0, self.lats[lo])
+                lat.peer_connect(1, self.lats[hi])
 
     def close(self):
         for lat in self.lats:
@@ -93,6 +112,8 @@ class EmulatedSlabs:
 
     def _exchange(self):
         import torch
+        if self.peer:  # the pack kernels have already written into the neighbours' mailboxes
+            return
         with torch.cuda.stream(self.stream):
             for r in range(self.world):
                 lo, hi = neighbours(self.world, r)
@@ -142,7 +163,7 @@ class EmulatedSlabs:
 class SlabLattice:
     """One rank's slab of a periodic nx*ny*nz box.  Mirrors Lattice (init_*, step, getters on the local slab)."""
 
-    def __init__(self, nx, ny, nz, params: Params | None = None, device: int = 0, group=None):
+    def __init__(self, nx, ny, nz, params: Params | None = None, device: int = 0, group=None, peer: bool = False):
         import torch
         import torch.distributed as dist
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -160,6 +181,20 @@ class SlabLattice:
         self.send = [_device_tensor(lib.bflbm_halo_send_buffer(h, s), n, self.device) for s in (0, 1)]
         self.recv = [_device_tensor(lib.bflbm_halo_recv_buffer(h, s), n, self.device) for s in (0, 1)]
         self.halo_bytes_per_step = 2 * n * 8
+        # peer mode: neighbours' mailboxes mapped through CUDA IPC; from then on a step needs no collective and no Python
+        self.peer = False
+        if peer:
+            self.connect_peers()
+
+    def connect_peers(self):
+        if self.world == 1:
+            self.lat.peer_connect(0, self.lat)
+            self.lat.peer_connect(1, self.lat)
+        else:
+            lo, hi = gather_ring_handles(self.lat.peer_ipc_handle(), self.rank, self.world, self.group)
+            self.lat.peer_connect_ipc(0, lo)
+            self.lat.peer_connect_ipc(1, hi)
+        self.peer = True
 
     # -- delegation --------------------------------------------------------------------------------
     def __getattr__(self, name):
@@ -167,6 +202,8 @@ class SlabLattice:
 
     def _exchange(self):
         import torch
+        if self.peer:
+            return
         with torch.cuda.stream(self.stream):
             exchange_ring(self.send[0], self.send[1], self.recv[0], self.recv[1], self.rank, self.world, self.group)
 
@@ -192,6 +229,9 @@ class SlabLattice:
 
     def step(self, n=1):
         lib, h = self.lat.lib, self.lat.h
+        if self.peer:  # the whole loop runs inside the library: begin (pack = NVLink stores), end (device-side wait, unpack)
+            _check(lib.bflbm_step_slab(h, int(n)))
+            return
         for _ in range(int(n)):
             _check(lib.bflbm_step_begin(h))
             self._exchange()

@@ -113,6 +113,45 @@ def load_library() -> ctypes.CDLL:
         "bflbm_second_moments": (ip, [vp, vp]),
         "bflbm_droplet_covariance": (ip, [vp, vp, vp, vp]),
         "bflbm_debug_philox": (ip, [vp, vp, vp]),
+        "bflbm_covariance_from_moments": (ip, [vp, vp, vp, vp]),
+        "bflbm_init_from_global_populations": (ip, [vp, vp, vp]),
+        "bflbm_get_populations_into_global": (ip, [vp, vp, vp]),
+        "bflbm_get_hydrovars_into_global": (ip, [vp, vp]),
+        "bflbm_get_hydrovars_bar_into_global": (ip, [vp, vp]),
+        "bflbm_get_noise_into_global": (ip, [vp, vp, vp]),
+        "bflbm_peer_mailbox_bytes": (ctypes.c_size_t, [vp]),
+        "bflbm_peer_mailbox": (vp, [vp]),
+        "bflbm_peer_ipc_handle": (ip, [vp, vp]),
+        "bflbm_peer_connect": (ip, [vp, ip, vp, ip]),
+        "bflbm_peer_connect_ipc": (ip, [vp, ip, vp]),
+        "bflbm_peer_connected": (ip, [vp]),
+        "bflbm_step_slab": (ip, [vp, ip]),
+        "bflbm_halo_refresh": (ip, [vp]),
+        "bflbm_halo_error": (ip, [vp, ctypes.POINTER(ip)]),
+        "bflbm_multi_create": (ip, [P, ip, ip, ip, ip, ctypes.POINTER(ip), ip, ctypes.POINTER(vp)]),
+        "bflbm_multi_destroy": (ip, [vp]),
+        "bflbm_multi_count": (ip, [vp]),
+        "bflbm_multi_slab": (vp, [vp, ip]),
+        "bflbm_multi_set_params": (ip, [vp, P]),
+        "bflbm_multi_init_mixture": (ip, [vp]),
+        "bflbm_multi_init_stripe": (ip, [vp, dp]),
+        "bflbm_multi_init_droplet": (ip, [vp, dp]),
+        "bflbm_multi_init_from_populations": (ip, [vp, vp, vp]),
+        "bflbm_multi_step": (ip, [vp, ip]),
+        "bflbm_multi_sync": (ip, [vp]),
+        "bflbm_multi_step_count": (ctypes.c_longlong, [vp]),
+        "bflbm_multi_get_populations": (ip, [vp, vp, vp]),
+        "bflbm_multi_get_hydrovars": (ip, [vp, vp]),
+        "bflbm_multi_get_hydrovars_bar": (ip, [vp, vp]),
+        "bflbm_multi_get_noise": (ip, [vp, vp, vp]),
+        "bflbm_multi_total_mass": (ip, [vp, vp, vp]),
+        "bflbm_multi_second_moments": (ip, [vp, vp]),
+        "bflbm_multi_center_of_mass": (ip, [vp, vp]),
+        "bflbm_multi_droplet_covariance": (ip, [vp, vp, vp, vp]),
+        "bflbm_multi_check_nan": (ip, [vp, ctypes.POINTER(ctypes.c_longlong)]),
+        "bflbm_multi_kernel_launches": (ctypes.c_longlong, [vp]),
+        "bflbm_multi_device_bytes": (ctypes.c_size_t, [vp]),
+        "bflbm_multi_last_error": (ctypes.c_char_p, []),
         "bflbm_last_error": (ctypes.c_char_p, []),
         "bflbm_version": (ctypes.c_char_p, []),
     }
@@ -215,6 +254,40 @@ class Lattice:
         g = _host(g_ghosted, shp, "g_ghosted")
         _check(self.lib.bflbm_init_from_populations_slab(self.h, f.ctypes.data, g.ctypes.data))
 
+    def init_from_global_populations(self, f_global, g_global):
+        """Host arrays of the WHOLE box (19, nz_global, ny, nx); a slab takes its planes and the periodic neighbour planes."""
+        shp = (NVEL, self.nz_global, self.ny, self.nx)
+        f = _host(f_global, shp, "f_global")
+        g = _host(g_global, shp, "g_global")
+        _check(self.lib.bflbm_init_from_global_populations(self.h, f.ctypes.data, g.ctypes.data))
+
+    # -- peer mode (include/bflbm.h): the halo message goes straight into the neighbour's mailbox ----------------
+    def peer_ipc_handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        _check(self.lib.bflbm_peer_ipc_handle(self.h, buf))
+        return buf.raw
+
+    def peer_connect_ipc(self, side: int, handle: bytes):
+        _check(self.lib.bflbm_peer_connect_ipc(self.h, int(side), ctypes.c_char_p(handle)))
+
+    def peer_connect(self, side: int, other: "Lattice"):
+        _check(self.lib.bflbm_peer_connect(self.h, int(side), ctypes.c_void_p(self.lib.bflbm_peer_mailbox(other.h)), int(other.device)))
+
+    @property
+    def peer_connected(self) -> bool:
+        return bool(self.lib.bflbm_peer_connected(self.h))
+
+    def step_slab(self, n=1):
+        _check(self.lib.bflbm_step_slab(self.h, int(n)))
+
+    def halo_refresh(self):
+        _check(self.lib.bflbm_halo_refresh(self.h))
+
+    def halo_error(self) -> int:
+        e = ctypes.c_int()
+        _check(self.lib.bflbm_halo_error(self.h, ctypes.byref(e)))
+        return e.value
+
     # -- time stepping --------------------------------------------------------------------------------
     def step(self, n=1):
         _check(self.lib.bflbm_step(self.h, int(n)))
@@ -299,6 +372,122 @@ class Lattice:
     @property
     def device_bytes(self) -> int:
         return int(self.lib.bflbm_device_bytes(self.h))
+
+
+class MultiLattice:
+    """One periodic box on several GPUs of this process (include/bflbm.h, bflbm_multi_*): z-slabs ring-connected in peer mode,
+    host arrays of the WHOLE box (ncomp, nz, ny, nx).  Mirrors Lattice."""
+
+    def __init__(self, nx, ny=None, nz=None, params: Params | None = None, ngpus: int = 1, devices=None, brick_lz: int = 0):
+        ny = nx if ny is None else ny
+        nz = nx if nz is None else nz
+        self.lib = load_library()
+        self.params = params or Params()
+        self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.shape = (self.nz, self.ny, self.nx)
+        self.ngpus = int(ngpus)
+        h = ctypes.c_void_p()
+        cp = self.params._c()
+        dev = (ctypes.c_int * self.ngpus)(*devices) if devices is not None else None
+        self._mcheck(self.lib.bflbm_multi_create(ctypes.byref(cp), self.nx, self.ny, self.nz, self.ngpus, dev, int(brick_lz), ctypes.byref(h)))
+        self.h = h
+
+    def _mcheck(self, rc):
+        if rc != 0:
+            raise BflbmError(f"bflbm error {rc}: {self.lib.bflbm_multi_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bflbm_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise AttributeError(k)
+            setattr(self.params, k, v)
+        cp = self.params._c()
+        self._mcheck(self.lib.bflbm_multi_set_params(self.h, ctypes.byref(cp)))
+
+    def init_mixture(self):
+        self._mcheck(self.lib.bflbm_multi_init_mixture(self.h))
+
+    def init_stripe(self, frac=0.5):
+        self._mcheck(self.lib.bflbm_multi_init_stripe(self.h, float(frac)))
+
+    def init_droplet(self, radius=0.2):
+        self._mcheck(self.lib.bflbm_multi_init_droplet(self.h, float(radius)))
+
+    def init_from_populations(self, f, g):
+        f = _host(f, (NVEL,) + self.shape, "f")
+        g = _host(g, (NVEL,) + self.shape, "g")
+        self._mcheck(self.lib.bflbm_multi_init_from_populations(self.h, f.ctypes.data, g.ctypes.data))
+
+    def step(self, n=1):
+        self._mcheck(self.lib.bflbm_multi_step(self.h, int(n)))
+
+    def sync(self):
+        self._mcheck(self.lib.bflbm_multi_sync(self.h))
+
+    @property
+    def step_count(self) -> int:
+        return int(self.lib.bflbm_multi_step_count(self.h))
+
+    def populations(self):
+        f, g = np.empty((NVEL,) + self.shape), np.empty((NVEL,) + self.shape)
+        self._mcheck(self.lib.bflbm_multi_get_populations(self.h, f.ctypes.data, g.ctypes.data))
+        return f, g
+
+    def hydrovars(self):
+        out = np.empty((NHYDRO,) + self.shape)
+        self._mcheck(self.lib.bflbm_multi_get_hydrovars(self.h, out.ctypes.data))
+        return out
+
+    def hydrovars_bar(self):
+        out = np.empty((NHYDRO_BAR,) + self.shape)
+        self._mcheck(self.lib.bflbm_multi_get_hydrovars_bar(self.h, out.ctypes.data))
+        return out
+
+    def noise(self):
+        fn, gn = np.empty((NVEL,) + self.shape), np.empty((NVEL,) + self.shape)
+        self._mcheck(self.lib.bflbm_multi_get_noise(self.h, fn.ctypes.data, gn.ctypes.data))
+        return fn, gn
+
+    def total_mass(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self._mcheck(self.lib.bflbm_multi_total_mass(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def droplet_covariance(self):
+        com, c6, e = np.empty(3), np.empty(6), np.empty(3)
+        self._mcheck(self.lib.bflbm_multi_droplet_covariance(self.h, com.ctypes.data, c6.ctypes.data, e.ctypes.data))
+        cov = np.array([[c6[0], c6[3], c6[4]], [c6[3], c6[1], c6[5]], [c6[4], c6[5], c6[2]]])
+        return com, cov, e
+
+    def check_nan(self) -> int:
+        n = ctypes.c_longlong()
+        self._mcheck(self.lib.bflbm_multi_check_nan(self.h, ctypes.byref(n)))
+        return n.value
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.bflbm_multi_kernel_launches(self.h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.bflbm_multi_device_bytes(self.h))
 
 
 def philox4x32_10(ctr, key):

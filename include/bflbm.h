@@ -125,6 +125,16 @@ int bflbm_get_hydrovars_device(bflbm_lattice* h, double* dev_out22);
 int bflbm_get_hydrovars_bar_device(bflbm_lattice* h, double* dev_out9);
 int bflbm_get_populations_device(bflbm_lattice* h, double* dev_f, double* dev_g);
 
+/* Host arrays of the WHOLE box, shape (ncomp, nz_global, ny, nx) -- the MultiFab a reference driver holds.  A slab reads /
+ * writes only its own planes [z0, z0 + nz_local) (for the restart also the two periodic neighbour planes), so every
+ * slab of a box can be pointed at the same arrays (ParallelCopy to / from a single-box MultiFab, AMReX_FileIO.H:18-34).
+ * After bflbm_init_from_global_populations a slab that is not in peer mode still needs the halo refresh. */
+int bflbm_init_from_global_populations(bflbm_lattice* h, const double* f_global, const double* g_global);
+int bflbm_get_populations_into_global(bflbm_lattice* h, double* f_global, double* g_global);
+int bflbm_get_hydrovars_into_global(bflbm_lattice* h, double* global22);
+int bflbm_get_hydrovars_bar_into_global(bflbm_lattice* h, double* global9);
+int bflbm_get_noise_into_global(bflbm_lattice* h, double* fn_global, double* gn_global);
+
 /* update_com  LBM_hydrovs.H:26-60 (centre of mass of rho; local-slab partial sums:
  * sums4 = {mass, sum rho*x, sum rho*y, sum rho*z_global}). */
 int bflbm_center_of_mass(bflbm_lattice* h, double* com3, double* sums4);
@@ -134,6 +144,8 @@ int bflbm_second_moments(bflbm_lattice* h, double* sums10);
 /* Whole box: centre of mass, mass-weighted covariance {xx, yy, zz, xy, xz, yz} of rho about it, and its eigenvalues in
  * ascending order (what fittingDropletCovariance returns per frame; Eigen there, closed form here).  Any output may be NULL. */
 int bflbm_droplet_covariance(bflbm_lattice* h, double* com3, double* cov6, double* eig3);
+/* The same from the ten sums (host arithmetic): add up bflbm_second_moments of all slabs of a box first. */
+int bflbm_covariance_from_moments(const double* sums10, double* com3, double* cov6, double* eig3);
 /* sums of rho and phi over the local cells (Debug.H:35-72 / main_run_job.cpp:224-228) */
 int bflbm_total_mass(bflbm_lattice* h, double* mass_rho, double* mass_phi);
 /* MultiFabNANCheck  Debug.H:136-149: counts non-finite values in the 22 hydro fields.
@@ -156,6 +168,63 @@ int bflbm_step_begin(bflbm_lattice* h);
 int bflbm_step_end(bflbm_lattice* h);
 int bflbm_halo_refresh_begin(bflbm_lattice* h);
 int bflbm_halo_refresh_end(bflbm_lattice* h);
+
+/* ---- peer mode: the exchange without the caller (replaces FillBoundary, LBM_binary.H:553-555, by stores over NVLink) -------
+ * Every slab lattice owns a "mailbox" in device memory (two receive slots per side + arrival flags).  Once both
+ * neighbours' mailboxes are connected, the pack kernel of bflbm_step_begin writes each message straight into the
+ * neighbour's mailbox (peer-mapped memory: NVLink / NVSwitch stores) and raises its flag; bflbm_step_end waits for the own
+ * flags on the device.  No NCCL, no copy kernel, no host synchronisation in the step loop.
+ *   same process, several devices : bflbm_peer_connect(h, side, bflbm_peer_mailbox(neighbour), neighbour's device)
+ *   one process per GPU           : exchange the 64-byte handles of bflbm_peer_ipc_handle out of band (torch.distributed,
+ *                                   MPI, a file) and call bflbm_peer_connect_ipc
+ * side 0 / 1 = the neighbour towards lower / higher z on the periodic ring.  All lattices of a box must make the same
+ * sequence of exchanges (steps, halo refreshes): messages carry a sequence number.
+ * Several slabs driven by ONE stream or one device must call _begin on all of them before the first _end (a wait would
+ * otherwise sit in front of the launch that satisfies it); slabs on different devices may use bflbm_step_slab. */
+#define BFLBM_IPC_HANDLE_BYTES 64
+size_t bflbm_peer_mailbox_bytes(const bflbm_lattice* h);
+void* bflbm_peer_mailbox(bflbm_lattice* h);
+int bflbm_peer_ipc_handle(bflbm_lattice* h, void* out64);
+int bflbm_peer_connect(bflbm_lattice* h, int side, void* neighbour_mailbox, int neighbour_device);
+int bflbm_peer_connect_ipc(bflbm_lattice* h, int side, const void* handle64);
+int bflbm_peer_connected(const bflbm_lattice* h);
+/* LBM_timestep nsteps times on a connected slab: (bflbm_step_begin, bflbm_step_end) x nsteps, asynchronous */
+int bflbm_step_slab(bflbm_lattice* h, int nsteps);
+/* bflbm_halo_refresh_begin + _end on a connected slab (after bflbm_init_from_populations_slab) */
+int bflbm_halo_refresh(bflbm_lattice* h);
+/* synchronises and reports whether a device-side wait for a neighbour's message ever timed out (10 s) */
+int bflbm_halo_error(bflbm_lattice* h, int* flag);
+
+/* ---- one box on several GPUs of ONE process (the `ngpus` a reference maintainer passes instead of setting up MPI ranks) -----
+ * Replaces BoxArray::maxSize + DistributionMapping + FillBoundary (main_run_job.cpp:140-145, LBM_binary.H:553-555): z-slabs,
+ * one per device, ring-connected in peer mode.  Host arrays are those of the WHOLE box, (ncomp, nz, ny, nx).  devices = NULL:
+ * devices 0 .. ngpus-1.  brick_lz = 0: automatic; results are bit-identical to the one-GPU run when both use the same
+ * brick height and it divides every slab.  ngpus = 1 is a plain whole-box lattice.  Errors: bflbm_multi_last_error(). */
+typedef struct bflbm_multi bflbm_multi;
+int bflbm_multi_create(const bflbm_params* p, int nx, int ny, int nz, int ngpus, const int* devices, int brick_lz, bflbm_multi** out);
+int bflbm_multi_destroy(bflbm_multi* m);
+int bflbm_multi_count(const bflbm_multi* m);
+bflbm_lattice* bflbm_multi_slab(bflbm_multi* m, int i); /* the i-th slab, e.g. for bflbm_get_dims */
+int bflbm_multi_set_params(bflbm_multi* m, const bflbm_params* p);
+int bflbm_multi_init_mixture(bflbm_multi* m);
+int bflbm_multi_init_stripe(bflbm_multi* m, double frac);
+int bflbm_multi_init_droplet(bflbm_multi* m, double radius);
+int bflbm_multi_init_from_populations(bflbm_multi* m, const double* f, const double* g);
+int bflbm_multi_step(bflbm_multi* m, int nsteps);
+int bflbm_multi_sync(bflbm_multi* m);
+long long bflbm_multi_step_count(const bflbm_multi* m);
+int bflbm_multi_get_populations(bflbm_multi* m, double* f, double* g);
+int bflbm_multi_get_hydrovars(bflbm_multi* m, double* out22);
+int bflbm_multi_get_hydrovars_bar(bflbm_multi* m, double* out9);
+int bflbm_multi_get_noise(bflbm_multi* m, double* fn, double* gn);
+int bflbm_multi_total_mass(bflbm_multi* m, double* mass_rho, double* mass_phi);
+int bflbm_multi_second_moments(bflbm_multi* m, double* sums10);
+int bflbm_multi_center_of_mass(bflbm_multi* m, double* com3);
+int bflbm_multi_droplet_covariance(bflbm_multi* m, double* com3, double* cov6, double* eig3);
+int bflbm_multi_check_nan(bflbm_multi* m, long long* count); /* also reports a timed-out halo wait */
+long long bflbm_multi_kernel_launches(const bflbm_multi* m);
+size_t bflbm_multi_device_bytes(const bflbm_multi* m);
+const char* bflbm_multi_last_error(void);
 
 /* Per-kernel device timing (CUDA events on the lattice's stream around each launch of a step):
  * ms4 = accumulated milliseconds of {collide+stream kernel, density fold / density pass, halo pack, halo unpack},

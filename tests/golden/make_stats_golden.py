@@ -7,7 +7,8 @@ The GPU tests (tests/test_gpu_statistics.py) run the same cases through the CUDA
 amrex::RandomNormal's stream is third-party and unpinned, so agreement is statistical by construction (SURVEY 8(c)).
 
 Run here (the container that has /root/reference):   python tests/golden/make_stats_golden.py [mixture|noise|capillary ...]
-Cases and cost on 8 host threads: mixture ~1 min, noise ~10 s, capillary ~20 min, droplet ~10 min.
+Cases and cost: mixture ~1 min, noise ~10 s on 8 host threads; capillary and droplet are ensembles of REPLICAS independent
+runs (different seeds, one host thread each, BFLBM_GOLDEN_WORKERS processes at a time): ~25 core-minutes per replica.
 """
 import json
 import os
@@ -32,6 +33,7 @@ CAPILLARY = dict(shape=(2, 32, 40), params=dict(kBT=1e-5, tau_f=0.5, tau_g=0.5, 
                  rho_lo=0.1, rho_hi=3.0, frac=0.5, det_steps=3000, equil=10000, steps=150000, every=100)
 DROPLET = dict(shape=(24, 24, 24), params=dict(kBT=2e-5, tau_f=0.5, tau_g=0.5, alpha0=1.5, alpha1=0.0, kappa=0.1), radius=0.3,
                rho_lo=0.1, rho_hi=3.0, det_steps=2000, equil=2000, steps=24000, every=40)
+REPLICAS = 16  # independent runs per ensemble case (round 1 had one run: +-25 % per capillary mode; 16 runs: +-10 %)
 SF_PAIRS = [(0, 0), (1, 1), (0, 1), (15, 15), (16, 16), (17, 17)]  # rho-rho, phi-phi, rho-phi, ub_a-ub_a
 
 
@@ -113,12 +115,53 @@ def run_droplet(stepper, rho_field, set_kbt, C=DROPLET):
             "sum_plus": plus, "sum_minus": minus, "frames": int(ax.shape[0])}
 
 
-def golden_droplet():
+def combine_capillary(runs, C=CAPILLARY):
+    """Ensemble of independent runs: every run removes its own mean height per column (Flat_Interface.ipynb cell 9), the spectra
+    are averaged with equal weights (equal frame counts)."""
+    k = np.array(runs[0]["k"])
+    p = np.mean([r["hk2"] for r in runs], axis=0)
+    nx, ny = C["shape"][0], C["shape"][1]
+    return {"h_det": runs[0]["h_det"], "h_mean": float(np.mean([r["h_mean"] for r in runs])), "k": k.tolist(), "hk2": p.tolist(),
+            "frames": int(sum(r["frames"] for r in runs)), "replicas": len(runs),
+            "gamma_lowk": stats.surface_tension_from_spectrum(k, p, C["params"]["kBT"], ny, nx, kmax=0.8)}
+
+
+def combine_droplet(runs):
+    return {"axes_det": runs[0]["axes_det"], "axes_mean": np.mean([r["axes_mean"] for r in runs], axis=0).tolist(),
+            "axes_var": np.mean([r["axes_var"] for r in runs], axis=0).tolist(), "sum_plus": float(np.mean([r["sum_plus"] for r in runs])),
+            "sum_minus": float(np.mean([r["sum_minus"] for r in runs])), "frames": int(sum(r["frames"] for r in runs)), "replicas": len(runs)}
+
+
+def _one_droplet(seed):
     C = DROPLET
-    O = ref(C["shape"], dict(C["params"], kBT=0.0), 1234)
+    O = ref(C["shape"], dict(C["params"], kBT=0.0), seed)
+    O.set_num_threads(1)
     f, g = om.droplet_populations(*C["shape"], C["radius"], C["params"]["kappa"], C["rho_lo"], C["rho_hi"])
     O.init_from_populations(f, g)
     return run_droplet(O.step, lambda: O.hydrovars_bar()[0], lambda kbt: O.set_params(kBT=kbt))
+
+
+def _one_capillary(seed):
+    C = CAPILLARY
+    O = ref(C["shape"], dict(C["params"], kBT=0.0), seed)
+    O.set_num_threads(1)
+    f, g = om.stripe_populations(*C["shape"], C["frac"], C["params"]["kappa"], C["rho_lo"], C["rho_hi"])
+    O.init_from_populations(f, g)
+    return run_capillary(O.step, lambda: O.hydrovars_bar()[0], lambda kbt: O.set_params(kBT=kbt))
+
+
+def _ensemble(fn, seed0):
+    import multiprocessing as mp
+    workers = int(os.environ.get("BFLBM_GOLDEN_WORKERS", "6"))
+    with mp.get_context("fork").Pool(workers) as pool:
+        return pool.map(fn, [seed0 + 1000 * i for i in range(REPLICAS)], chunksize=1)
+
+
+def golden_droplet():
+    runs = _ensemble(_one_droplet, 1234)
+    out = combine_droplet(runs)
+    out["per_replica"] = [{"sum_plus": r["sum_plus"], "sum_minus": r["sum_minus"]} for r in runs]
+    return out
 
 
 def golden_mixture():
@@ -144,11 +187,10 @@ def golden_noise():
 
 
 def golden_capillary():
-    C = CAPILLARY
-    O = ref(C["shape"], dict(C["params"], kBT=0.0), 99)
-    f, g = om.stripe_populations(*C["shape"], C["frac"], C["params"]["kappa"], C["rho_lo"], C["rho_hi"])
-    O.init_from_populations(f, g)
-    return run_capillary(O.step, lambda: O.hydrovars_bar()[0], lambda kbt: O.set_params(kBT=kbt))
+    runs = _ensemble(_one_capillary, 99)
+    out = combine_capillary(runs)
+    out["per_replica_hk2"] = [r["hk2"] for r in runs]
+    return out
 
 
 if __name__ == "__main__":

@@ -21,7 +21,8 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     nx, ny, nz, lz = 40, 24, 24 * world, 4
     prm = b.Params(kBT=1e-5, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, tau_f=0.7, tau_g=0.55, seed=4711)
-    S = SlabLattice(nx, ny, nz, params=prm, device=local)
+    peer = os.environ.get("MP_PEER", "0") == "1"  # halo messages as peer-to-peer stores through CUDA-IPC-mapped mailboxes
+    S = SlabLattice(nx, ny, nz, params=prm, device=local, peer=peer)
     S.lat.set_tiling(lz)
     S.init_droplet(0.3)
     with b.Lattice(nx, ny, nz, params=prm, device=local) as whole:
@@ -36,13 +37,27 @@ def main():
             sl = slice(S.z0, S.z0 + S.nzl)
             ok &= np.array_equal(fw[:, sl], fs) and np.array_equal(gw[:, sl], gs)
             ok &= np.array_equal(whole.hydrovars()[:, sl], S.lat.hydrovars())
+        # restart through the whole-box host arrays (every rank points at the same global array), then step again
+        S.lat.init_from_global_populations(fw, gw)
+        if peer:
+            b.lattice._check(S.lat.lib.bflbm_halo_refresh_end(S.lat.h))
+        else:
+            b.lattice._check(S.lat.lib.bflbm_halo_refresh_begin(S.lat.h))
+            S._exchange()
+            b.lattice._check(S.lat.lib.bflbm_halo_refresh_end(S.lat.h))
+        whole.init_from_populations(fw, gw)
+        S.step(3)
+        whole.step(3)
+        ok &= np.array_equal(whole.hydrovars()[:, sl], S.lat.hydrovars())
+        if peer:
+            ok &= S.lat.halo_error() == 0
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     S.lat.close()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
-        print("MP_SLAB_OK" if int(t.item()) == 1 else "MP_SLAB_MISMATCH", world, flush=True)
+        print("MP_SLAB_OK" if int(t.item()) == 1 else "MP_SLAB_MISMATCH", world, "peer" if peer else "nccl", flush=True)
     sys.exit(0 if int(t.item()) == 1 else 1)
 
 

@@ -288,20 +288,23 @@ def test_center_of_mass_and_mass(bflbm, oracle_mod):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # slab decomposition (the multi-GPU path), emulated on one GPU: P slabs, device-to-device copies instead of NCCL
+@pytest.mark.parametrize("peer", [False, True], ids=["copies", "peer"])
 @pytest.mark.parametrize("lz", [2, 4])
 @pytest.mark.parametrize("nslabs", [2, 3, 4])
 @pytest.mark.parametrize("kbt", [0.0, 1e-5])
-def test_slabs_bitwise_equal_to_whole_box(bflbm, nslabs, kbt, lz):
+def test_slabs_bitwise_equal_to_whole_box(bflbm, nslabs, kbt, lz, peer):
     """results must not depend on the number of slabs.  Same brick height => bit-identical.
     Slabs have >= 3 brick rows, so the overlapped step (end rows + exchange on one stream, interior rows on a second)
-    is the path under test; lz = 4 adds planes that the step kernel folds itself from the extended boxes."""
+    is the path under test; lz = 4 adds planes that the step kernel folds itself from the extended boxes.
+    peer: the pack kernel writes each message straight into the neighbour lattice's mailbox and raises its arrival flag,
+    the unpack kernel waits for the flag on the device (the multi-GPU protocol, here between lattices of one GPU)."""
     from bflbm_b200.distributed import EmulatedSlabs
     shape = (20, 12, 48)
     prm = bflbm.Params(kBT=kbt, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, tau_f=0.7, tau_g=0.55, seed=99)
     with bflbm.Lattice(*shape, params=prm) as whole:
         whole.set_tiling(lz)
         whole.init_droplet(0.3)
-        S = EmulatedSlabs(*shape, nslabs, params=prm, brick_lz=lz)
+        S = EmulatedSlabs(*shape, nslabs, params=prm, brick_lz=lz, peer=peer)
         try:
             S.init_droplet(0.3)
             for _ in range(3):
@@ -313,6 +316,8 @@ def test_slabs_bitwise_equal_to_whole_box(bflbm, nslabs, kbt, lz):
                 assert np.array_equal(whole.hydrovars(), S.gather("hydrovars"))
             if kbt > 0:
                 assert np.array_equal(whole.normals(), S.gather("normals")), "noise is keyed by the GLOBAL cell index"
+            if peer:
+                assert all(lat.halo_error() == 0 for lat in S.lats)
         finally:
             S.close()
 
@@ -342,6 +347,62 @@ def test_slabs_with_one_plane_last_brick_row(bflbm):
             S.close()
     assert np.array_equal(runs[0], runs[1]), "slab step is not reproducible run to run"
     assert_hydro_close(runs[0], want, 1e-11, "slabs with a one-plane last brick row")
+
+
+def test_global_array_entry_points_on_slabs(bflbm, oracle_mod):
+    """bflbm_init_from_global_populations / bflbm_get_*_into_global: every slab is pointed at the WHOLE box's host arrays and
+    reads / fills only its planes (the wrap-around ghost planes of the first and last slab included)."""
+    from bflbm_b200.distributed import EmulatedSlabs
+    shape = (12, 10, 17)
+    prm = dict(kBT=0.0, tau_f=0.5, tau_g=0.5, alpha0=1.5, alpha1=0.0, kappa=0.1, rho_lo=0.1, rho_hi=3.0)
+    O = oracle_mod.PortOracle(*shape)
+    O.set_params(**prm)
+    O.init_droplet(0.3)
+    O.step(2)
+    f, g = O.populations()
+    S = EmulatedSlabs(*shape, 3, params=bflbm.Params(**prm), peer=True)
+    try:
+        for lat in S.lats:
+            lat.init_from_global_populations(f, g)  # peer mode: uploads and packs
+        for lat in S.lats:
+            bflbm.lattice._check(lat.lib.bflbm_halo_refresh_end(lat.h))
+        S.step(3)
+        O.step(3)
+        h = np.full((22,) + shape[::-1], np.nan)
+        fo, go = np.full_like(f, np.nan), np.full_like(g, np.nan)
+        for lat in S.lats:
+            bflbm.lattice._check(lat.lib.bflbm_get_hydrovars_into_global(lat.h, h.ctypes.data))
+            bflbm.lattice._check(lat.lib.bflbm_get_populations_into_global(lat.h, fo.ctypes.data, go.ctypes.data))
+        assert np.array_equal(h, S.gather("hydrovars")) and np.array_equal(fo, S.gather("populations")[0])
+        assert_hydro_close(h, O.hydrovars(), 10 * TOL, "global-array restart + 3 steps")
+    finally:
+        S.close()
+    with bflbm.Lattice(*shape, params=bflbm.Params(**prm)) as W:  # the same entry point on a whole box
+        W.init_from_global_populations(f, g)
+        W.step(3)
+        assert_hydro_close(W.hydrovars(), O.hydrovars(), 10 * TOL, "whole box through the global-array entry")
+
+
+def test_multi_with_one_gpu_is_the_whole_box(bflbm):
+    """bflbm_multi with ngpus = 1 is a plain whole-box lattice (same bits); N > 1 is covered by tests/test_gpu_multiprocess.py."""
+    shape = (16, 12, 20)
+    prm = bflbm.Params(kBT=1e-5, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, seed=3)
+    with bflbm.Lattice(*shape, params=prm) as A, bflbm.MultiLattice(*shape, params=prm, ngpus=1) as M:
+        A.init_droplet(0.3)
+        M.init_droplet(0.3)
+        A.step(7)
+        M.step(7)
+        assert np.array_equal(A.hydrovars(), M.hydrovars()) and M.step_count == 7
+        fa, ga = A.populations()
+        M.init_from_populations(fa, ga)
+        A.init_from_populations(fa, ga)
+        A.step(2)
+        M.step(2)
+        assert np.array_equal(A.hydrovars_bar(), M.hydrovars_bar())
+        assert np.allclose(A.total_mass(), M.total_mass(), rtol=1e-14)
+        assert M.check_nan() == 0
+        ca, cb = A.droplet_covariance(), M.droplet_covariance()
+        assert all(np.array_equal(x, y) for x, y in zip(ca, cb))
 
 
 def test_slabs_restart_from_populations(bflbm, oracle_mod):
@@ -383,6 +444,38 @@ def test_rate1_fast_path_matches_general_path(bflbm, monkeypatch, kbt):
             fb, gb = B.populations()
             assert np.abs(fa - fb).max() <= 1e-14 * np.abs(fb).max()
             assert np.abs(ga - gb).max() <= 1e-14 * np.abs(gb).max()
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("kbt", [0.0, 1e-5])
+@pytest.mark.parametrize("shape", [(32, 32, 32), (8, 40, 24)])
+def test_graph_replayed_steps_bitwise_equal_to_single_launches(bflbm, monkeypatch, kbt, shape, algo):
+    """bflbm_step(n) replays CUDA graphs of 64 / 16 / 4 / 2 steps once the lattice is in steady state (small boxes are
+    launch bound: Parameters:1-37).  The noise key's step counter then comes from device memory.  Same bits as stepping
+    with plain launches (BFLBM_GRAPH=0), whatever the split into calls."""
+    prm = dict(kBT=kbt, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, tau_f=0.5, tau_g=0.5, seed=2024)
+    monkeypatch.setenv("BFLBM_GRAPH", "0")
+    with make_lattice(bflbm, shape, prm, algo) as P:
+        monkeypatch.delenv("BFLBM_GRAPH")
+        with make_lattice(bflbm, shape, prm, algo) as Gr:
+            P.init_droplet(0.3)
+            Gr.init_droplet(0.3)
+            l0 = Gr.kernel_launches
+            for n in (1, 87, 2, 5, 64):  # 87 = 64 + 16 + 4 + 2 + 1
+                P.step(n)
+                Gr.step(n)
+                fp, gp = P.populations()
+                fg, gg = Gr.populations()
+                assert np.array_equal(fp, fg) and np.array_equal(gp, gg), f"graph replay differs after a call of {n} steps"
+                assert np.array_equal(P.hydrovars(), Gr.hydrovars())
+            assert Gr.step_count == P.step_count == 159
+            # changing kBT re-captures (the parameters are by-value arguments of the captured launches)
+            P.set_params(kBT=2e-5)
+            Gr.set_params(kBT=2e-5)
+            P.step(20)
+            Gr.step(20)
+            assert np.array_equal(P.hydrovars(), Gr.hydrovars())
+            assert Gr.kernel_launches > l0
 
 
 def test_droplet_covariance_matches_numpy(bflbm):
