@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/bflbm.h"
+#include "droplet_fit.hpp"
 #include "fused.cuh"
 #include "kernels.cuh"
 
@@ -101,12 +102,20 @@ struct bflbm_lattice {
   // captured chunk can be replayed; d_step_host mirrors the value it will have once everything queued has run.
   bool use_graphs = true;  // BFLBM_GRAPH=0 disables
   std::map<long long, cudaGraphExec_t> graphs;
+  std::map<long long, long long> graph_nodes;  // kernel nodes per graph (launch bookkeeping)
   long long* d_step = nullptr;
   long long d_step_host = -1;
   bool in_graph_capture = false;
   int graph_step_off = 0, graph_bump = 0;
   bool wrapped_in_fold = false;
   bool ghosts_stale = false;  // two-pass steps leave the ghost planes of X and R behind
+
+  // USE_REF_STATE noise (LBM_binary.H:12, 92-107; bflbm_set_reference_state): equilibrium profiles [rho_eq | phi_eq | rhot_eq], the
+  // centre of mass of rho_eq, and the integer shift (com - com_ref) the device recomputes after every step
+  double* eq = nullptr;
+  int* d_shift = nullptr;
+  double com_ref[3] = {0., 0., 0.};
+  bool ref_relative = true;  // false after an analytic init: those pass the ABSOLUTE centre of mass (LBM_binary.H:623-625)
 
   // optional per-kernel timing: events ev[0..4] bracket {step kernel, fold, pack, unpack}
   bool profiling = false;
@@ -247,6 +256,17 @@ int chunk_planes(const bflbm_lattice* h, int ncomp, int extra_planes) {
 }
 
 dim3 cell_grid(const bflbm_lattice* h, int planes) { return dim3(h->grid_xy.x, h->grid_xy.y, planes); }
+RefState rs_of(const bflbm_lattice* h) { return RefState{h->eq, h->d_shift}; }
+// update_com + shift for the reference-state noise; R must be complete (two-pass kernels: always)
+int update_ref_shift(bflbm_lattice* h) {
+  if (!h->eq) return 0;
+  k_diag<<<cell_grid(h, h->G.nzl), h->block, 0, h->stream>>>(h->G, h->R, h->diag_partial, h->diag_count);
+  const double cx = h->ref_relative ? h->com_ref[0] : 0., cy = h->ref_relative ? h->com_ref[1] : 0., cz = h->ref_relative ? h->com_ref[2] : 0.;
+  k_com_shift<<<1, 256, 0, h->stream>>>(h->diag_partial, (long long)h->diag_blocks, cx, cy, cz, h->d_shift);
+  h->launches += 2;
+  CU(cudaGetLastError());
+  return 0;
+}
 
 // ---- ghost planes of a whole-box lattice (periodic in z inside one GPU) --------------------------------
 int wrap_population_ghosts(bflbm_lattice* h, double* X) {
@@ -332,7 +352,7 @@ int pack_halo(bflbm_lattice* h) {
   }
   P.seq = h->halo_seq;
   P.done = mailbox_done(h->mailbox, h);
-  const dim3 grid((unsigned)((G.plane + 255) / 256), 14, 2);
+  const dim3 grid((unsigned)((G.plane + 256 * HALO_PER_THREAD - 1) / (256 * HALO_PER_THREAD)), 14, 2);
   k_pack_halo<<<grid, 256, 0, h->stream>>>(P, h->X[h->cur], (const double*)h->R, G.plane);
   ++h->launches;
   CU(cudaGetLastError());
@@ -363,7 +383,7 @@ int unpack_halo(bflbm_lattice* h, double* const recv[2]) {
   }
   U.seq = h->halo_seq;
   U.err = mailbox_err(h->mailbox, h);
-  const dim3 grid((unsigned)((G.plane + 255) / 256), 11, 2);
+  const dim3 grid((unsigned)((G.plane + 256 * HALO_PER_THREAD - 1) / (256 * HALO_PER_THREAD)), 11, 2);
   k_unpack_halo<<<grid, 256, 0, h->stream>>>(U, h->X[h->cur], h->R, G.plane);
   ++h->launches;
   CU(cudaGetLastError());
@@ -446,7 +466,7 @@ int step_local(bflbm_lattice* h, bool pack = true) {
     const long long* sdev = h->in_graph_capture ? h->d_step : nullptr;
     const bool rate1 = h->rate1_fast_path && h->dp.rate_f == 1. && h->dp.rate_g == 1.;
     const dim3 grid = cell_grid(h, h->G.nzl);
-#define BFLBM_TP(N, R1) k_step_twopass<N, R1><<<grid, h->block, 0, h->stream>>>(h->G, h->dp, step, sdev, h->X[h->cur], h->X[1 - h->cur], h->R)
+#define BFLBM_TP(N, R1) k_step_twopass<N, R1><<<grid, h->block, 0, h->stream>>>(h->G, h->dp, step, sdev, h->X[h->cur], h->X[1 - h->cur], h->R, rs_of(h))
     if (noise) { if (rate1) BFLBM_TP(true, true); else BFLBM_TP(true, false); }
     else       { if (rate1) BFLBM_TP(false, true); else BFLBM_TP(false, false); }
 #undef BFLBM_TP
@@ -458,6 +478,8 @@ int step_local(bflbm_lattice* h, bool pack = true) {
     k_density<<<cell_grid(h, h->G.nzl), h->block, 0, h->stream>>>(h->G, h->X[h->cur], h->R, h->graph_bump > 0 ? h->d_step : nullptr, h->graph_bump);
     ++h->launches;
     CU(cudaGetLastError());
+    h->ref_relative = true;  // LBM_timestep passes com - com_ref (LBM_binary.H:586-588)
+    if ((rc0 = update_ref_shift(h))) return rc0;
     mark(h, 2);
     mark(h, 3);
     return 0;
@@ -537,6 +559,7 @@ int run_graph_chunk(bflbm_lattice* h, int K) {
     }
     h->in_graph_capture = false;
     h->graph_bump = 0;
+    h->graph_nodes[key] = h->launches - launches0;
     h->launches = launches0;
     const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
     if (rc || e != cudaSuccess || !g) {
@@ -557,7 +580,7 @@ int run_graph_chunk(bflbm_lattice* h, int K) {
     h->d_step_host = h->step;
   }
   CU(cudaGraphLaunch(it->second, h->stream));
-  h->launches += 2 * K;
+  h->launches += h->graph_nodes[key];
   h->step += K;
   h->d_step_host += K;
   if (h->algo == 0) {
@@ -673,6 +696,7 @@ int finish_init(bflbm_lattice* h) {
   h->initialized = true;
   h->e_valid = false;  // R was (or is about to be) rebuilt from the populations; E is void
   h->r_stale = false;
+  h->ghosts_stale = false;
   return 0;
 }
 
@@ -682,7 +706,9 @@ int run_init(bflbm_lattice* h, const InitSpec& S) {
   k_init<<<cell_grid(h, h->G.nzl + 2), h->block, 0, h->stream>>>(h->G, S, h->X[h->cur], h->R);
   ++h->launches;
   CU(cudaGetLastError());
-  return finish_init(h);
+  if ((rc = finish_init(h))) return rc;
+  h->ref_relative = false;  // the analytic inits hand thermal_noise the absolute centre of mass (LBM_binary.H:623-625)
+  return update_ref_shift(h);
 }
 
 // generic chunked observer -> host (or device) array of ncomp components
@@ -700,8 +726,8 @@ int observe(bflbm_lattice* h, int ncomp, double* out, bool out_is_device, bool c
   if ((rc = ensure_stage(h, (size_t)ncomp * cp * G.plane))) return rc;
   for (int zlo = 0; zlo < G.nzl; zlo += cp) {
     const int zc = std::min(cp, G.nzl - zlo);
-    if (noise) k_observe<MODE, true><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage);
-    else       k_observe<MODE, false><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage);
+    if (noise) k_observe<MODE, true><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage, rs_of(h));
+    else       k_observe<MODE, false><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage, rs_of(h));
     ++h->launches;
     CU(cudaGetLastError());
     const cudaMemcpyKind kind = out_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -778,8 +804,8 @@ int observe_pair(bflbm_lattice* h, double* a, double* b, bool into_global) {
   const size_t z_off = into_global ? (size_t)G.z0 : 0, comp_planes = into_global ? (size_t)G.nz_global : (size_t)G.nzl;
   for (int zlo = 0; zlo < G.nzl; zlo += cp) {
     const int zc = std::min(cp, G.nzl - zlo);
-    if (noise) k_observe<MODE, true><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage);
-    else       k_observe<MODE, false><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage);
+    if (noise) k_observe<MODE, true><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage, rs_of(h));
+    else       k_observe<MODE, false><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage, rs_of(h));
     ++h->launches;
     CU(cudaGetLastError());
     double* outs[2] = {a, b};
@@ -815,6 +841,8 @@ int bflbm_destroy(bflbm_lattice* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   drop_graphs(h);
   cudaFree(h->d_step);
+  cudaFree(h->eq);
+  cudaFree(h->d_shift);
   if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
   if (h->ev_prev) cudaEventDestroy(h->ev_prev);
   if (h->ev_ends) cudaEventDestroy(h->ev_ends);
@@ -865,6 +893,7 @@ int bflbm_set_algorithm(bflbm_lattice* h, int algo) {
   CHECK_H(h);
   if (algo < 0 || algo > 1) return fail(BFLBM_ERR_ARG, "algorithm must be 0 (fused one-pass) or 1 (two-pass)");
   if (algo == 1 && !h->whole_box) return fail(BFLBM_ERR_ARG, "the two-pass algorithm supports whole-box lattices only");
+  if (algo == 0 && h->eq) return fail(BFLBM_ERR_STATE, "the reference-state noise runs on the two-pass kernels (bflbm_set_reference_state(h, NULL, NULL, NULL) first)");
   h->algo = algo;
   h->algo_auto = false;
   return bflbm_set_tiling(h, h->lz_request);  // the brick shape depends on the kernel
@@ -956,6 +985,55 @@ int bflbm_init_from_global_populations(bflbm_lattice* h, const double* f_global,
   return 0;
 }
 
+int bflbm_set_reference_state(bflbm_lattice* h, const double* rho_eq, const double* phi_eq, const double* rhot_eq) {
+  CHECK_H(h);
+  int rc = set_device(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  drop_graphs(h);
+  if (!rho_eq) {  // back to the shipped behaviour: amplitudes from the current densities
+    cudaFree(h->eq);
+    h->eq = nullptr;
+    return 0;
+  }
+  if (!phi_eq || !rhot_eq) return fail(BFLBM_ERR_ARG, "null equilibrium field");
+  if (!h->whole_box) return fail(BFLBM_ERR_ARG, "the reference-state noise needs the centre of mass of the whole box every step: whole-box lattices only");
+  const size_t n = (size_t)h->G.plane * h->G.nzl;
+  if (!h->eq) {
+    CU(cudaMalloc((void**)&h->eq, 3 * n * sizeof(double)));
+    if (!h->d_shift) CU(cudaMalloc((void**)&h->d_shift, 3 * sizeof(int)));
+    CU(cudaMemset(h->d_shift, 0, 3 * sizeof(int)));
+  }
+  const double* src[3] = {rho_eq, phi_eq, rhot_eq};
+  for (int k = 0; k < 3; ++k) CU(cudaMemcpy(h->eq + k * n, src[k], n * sizeof(double), cudaMemcpyHostToDevice));
+  // com_ref[0] = update_com(rho_eq), main_run_job.cpp:229-233: cells visited x fastest
+  double m = 0., sx = 0., sy = 0., sz = 0.;
+  size_t c = 0;
+  for (int k = 0; k < h->G.nzl; ++k)
+    for (int j = 0; j < h->G.ny; ++j)
+      for (int i = 0; i < h->G.nx; ++i, ++c) {
+        const double r = rho_eq[c];
+        m += r; sx += r * i; sy += r * j; sz += r * k;
+      }
+  h->com_ref[0] = sx / m; h->com_ref[1] = sy / m; h->com_ref[2] = sz / m;
+  // the shift comes from the density field R of the thread-per-cell kernels
+  if (h->algo != 1) {
+    if (h->initialized && (rc = ensure_full_R(h))) return rc;
+    h->algo = 1;
+    h->algo_auto = false;
+    h->e_valid = false;
+  }
+  if (h->initialized && (rc = update_ref_shift(h))) return rc;
+  return 0;
+}
+int bflbm_get_reference_com(const bflbm_lattice* h, double* com3) {
+  CHECK_H(h);
+  if (!com3) return fail(BFLBM_ERR_ARG, "null output");
+  if (!h->eq) return fail(BFLBM_ERR_STATE, "no reference state set");
+  for (int k = 0; k < 3; ++k) com3[k] = h->com_ref[k];
+  return 0;
+}
+
 int bflbm_step(bflbm_lattice* h, int nsteps) {
   CHECK_H(h);
   if (!h->initialized) return fail(BFLBM_ERR_STATE, "bflbm_step before init");
@@ -1026,7 +1104,9 @@ int bflbm_halo_refresh_end(bflbm_lattice* h) {
   int rc = set_device(h);
   if (rc) return rc;
   double* const self[2] = {h->send[1], h->send[0]};
-  return unpack_halo(h, h->whole_box ? self : h->recv);
+  if ((rc = unpack_halo(h, h->whole_box ? self : h->recv))) return rc;
+  h->ref_relative = true;  // restart entry: LBM_init passes com - com_ref (LBM_binary.H:651-653)
+  return update_ref_shift(h);
 }
 size_t bflbm_halo_doubles(const bflbm_lattice* h) { return h ? h->halo_doubles : 0; }
 void* bflbm_halo_send_buffer(bflbm_lattice* h, int side) { return (h && (side == 0 || side == 1)) ? h->send[side] : nullptr; }
@@ -1166,7 +1246,7 @@ int bflbm_get_populations_device(bflbm_lattice* h, double* dev_f, double* dev_g)
   if ((rc = ensure_stage(h, (size_t)(2 * Q) * cp * G.plane))) return rc;
   for (int zlo = 0; zlo < G.nzl; zlo += cp) {
     const int zc = std::min(cp, G.nzl - zlo);
-    k_observe<OBS_POP, false><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage);
+    k_observe<OBS_POP, false><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage, rs_of(h));
     ++h->launches;
     CU(cudaGetLastError());
     double* outs[2] = {dev_f, dev_g};
@@ -1272,6 +1352,69 @@ int bflbm_droplet_covariance(bflbm_lattice* h, double* com3, double* cov6, doubl
   if (rc) return rc;
   return bflbm_covariance_from_moments(m, com3, cov6, eig3);
 }
+// ---- droplet (W, R) fit, SURVEY 8(f) row 4 (droplet_fit.hpp) ---------------------------------------------------------------------
+// local partial sums over this lattice's cells: sums4 = {sum rho (R - r') sech^2, sum rho sech^2, min rho, max rho}
+int bflbm_droplet_fit_terms(bflbm_lattice* h, double W, double Rn, const double* r0, double* sums4) {
+  CHECK_H(h);
+  if (!r0 || !sums4) return fail(BFLBM_ERR_ARG, "null argument");
+  if (!(W > 0.)) return fail(BFLBM_ERR_ARG, "W must be > 0");
+  if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = ensure_full_R(h))) return rc;
+  k_fit_terms<<<cell_grid(h, h->G.nzl), h->block, 0, h->stream>>>(h->G, h->R, 1. / sqrt(2. * W), Rn, r0[0], r0[1], r0[2], h->diag_partial);
+  ++h->launches;
+  CU(cudaGetLastError());
+  static_assert(NDIAG >= 4, "the diagnostics buffer holds at least four values per block");
+  std::vector<double> part(h->diag_blocks * 4);
+  CU(cudaMemcpyAsync(part.data(), h->diag_partial, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  sums4[0] = sums4[1] = 0.;
+  sums4[2] = 1e300;
+  sums4[3] = -1e300;
+  for (size_t b = 0; b < h->diag_blocks; ++b) {  // block order: the same sum on every run
+    sums4[0] += part[b * 4];
+    sums4[1] += part[b * 4 + 1];
+    sums4[2] = std::min(sums4[2], part[b * 4 + 2]);
+    sums4[3] = std::max(sums4[3], part[b * 4 + 3]);
+  }
+  return 0;
+}
+int bflbm_fit_droplet(bflbm_lattice* h, int step_window, double undul_ratio, int nstep, double W0, double R0, double eta_W, double eta_R,
+                      double dt, double* out3, int* converged) {
+  CHECK_H(h);
+  if (!out3) return fail(BFLBM_ERR_ARG, "null output");
+  if (!h->whole_box) return fail(BFLBM_ERR_ARG, "slab lattice: use bflbm_multi_fit_droplet (or combine bflbm_droplet_fit_terms of all slabs)");
+  if (nstep < 2 || step_window < 1 || step_window > nstep || !(W0 > 0.)) return fail(BFLBM_ERR_ARG, "bad fit parameters");
+  double com[3];
+  int rc = bflbm_center_of_mass(h, com, nullptr);  // cell indices; cell centres in the unit cube: (i + 1/2) / n (LBM_hydrovs.H:92-96)
+  if (rc) return rc;
+  const double r0[3] = {(com[0] + 0.5) / h->G.nx, (com[1] + 0.5) / h->G.ny, (com[2] + 0.5) / h->G.nz_global};
+  double s4[4];
+  if ((rc = bflbm_droplet_fit_terms(h, W0, R0, r0, s4))) return rc;
+  const double range = s4[3] - s4[2];
+  fit::FieldTerms terms = [h](double W, double R, const double* c, double* sums) {
+    double t[4];
+    const int e = bflbm_droplet_fit_terms(h, W, R, c, t);
+    sums[0] = t[0];
+    sums[1] = t[1];
+    return e;
+  };
+  fit::Result res;
+  const double vol = 1. / ((double)h->G.nx * h->G.ny * h->G.nz_global);
+  if ((rc = fit::fit(terms, vol, r0, range, step_window, undul_ratio, nstep, W0, R0, eta_W, eta_R, dt, res))) return rc;
+  out3[0] = res.W; out3[1] = res.R; out3[2] = res.undulation;
+  if (converged) *converged = res.converged ? 1 : 0;
+  return 0;
+}
+// the closed-form coefficients of one flow step (test hook: pure host arithmetic, runs without a GPU)
+int bflbm_debug_fit_coefficients(double W, double R, double eta_W, double eta_R, double dt, double C0, double* out6) {
+  if (!out6 || !(W > 0.)) return fail(BFLBM_ERR_ARG, "bad argument");
+  const fit::Coefficients q = fit::coefficients(W, R, eta_W, eta_R, dt, C0, fit::sech4_coefficients(fit::SERIES_TERMS));
+  out6[0] = q.JRR; out6[1] = q.JWR; out6[2] = q.JRW; out6[3] = q.JWW; out6[4] = q.KW; out6[5] = q.KR;
+  return 0;
+}
+
 int bflbm_check_nan(bflbm_lattice* h, long long* count) {
   CHECK_H(h);
   if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
@@ -1285,8 +1428,8 @@ int bflbm_check_nan(bflbm_lattice* h, long long* count) {
   CU(cudaMemsetAsync(h->diag_count, 0, sizeof(unsigned long long), h->stream));
   for (int zlo = 0; zlo < G.nzl; zlo += cp) {
     const int zc = std::min(cp, G.nzl - zlo);
-    if (noise) k_observe<OBS_HYDRO, true><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage);
-    else       k_observe<OBS_HYDRO, false><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage);
+    if (noise) k_observe<OBS_HYDRO, true><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage, rs_of(h));
+    else       k_observe<OBS_HYDRO, false><<<cell_grid(h, zc), h->block, 0, h->stream>>>(G, h->dp, h->step, zlo, h->X[h->cur], h->R, h->stage, rs_of(h));
     const long long n = (long long)BFLBM_NHYDRO * zc * G.plane;
     k_count_nonfinite<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->stage, n, h->diag_count);
     h->launches += 2;

@@ -713,21 +713,26 @@ struct HaloPack {
   unsigned long long seq;
   unsigned int* done;              // CTA counter of this lattice (peer mode)
 };
+constexpr int HALO_PER_THREAD = 8;  // elements per thread of the pack / unpack kernels (one CTA = 2048 consecutive cells of a plane)
 __global__ void __launch_bounds__(256) k_pack_halo(const __grid_constant__ HaloPack H, const double* __restrict__ X,
                                                     const double* __restrict__ R, long long plane) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y, side = blockIdx.z;
-  if (i < plane) {
-    double v;
-    if (j < 10) v = X[H.pop_src[side][j] + i];
-    else if (j < 12) v = R[H.r_bnd[side] + (long long)(j - 10) * plane + i];
-    else v = R[H.r_out[side] + (long long)(j - 12) * plane + i];
-    H.dst[side][(long long)j * plane + i] = v;
-  }
+  const double* src = j < 10 ? X + H.pop_src[side][j] : (j < 12 ? R + H.r_bnd[side] + (long long)(j - 10) * plane
+                                                                    : R + H.r_out[side] + (long long)(j - 12) * plane);
+  double* dst = H.dst[side] + (long long)j * plane;
+  const long long i0 = (long long)blockIdx.x * (256 * HALO_PER_THREAD) + threadIdx.x;
+  double v[HALO_PER_THREAD];
+#pragma unroll
+  for (int k = 0; k < HALO_PER_THREAD; ++k) v[k] = i0 + k * 256 < plane ? src[i0 + k * 256] : 0.;
+#pragma unroll
+  for (int k = 0; k < HALO_PER_THREAD; ++k)
+    if (i0 + k * 256 < plane) dst[i0 + k * 256] = v[k];
   if (H.flag[0] != nullptr) {
-    __threadfence_system();  // my store is visible system-wide before anything I (or a thread that observes me) do next
+    // the CTA's stores happen before the barrier; thread 0's system-scope fence is cumulative over what it has observed, so the
+    // counter increment -- and, from the last CTA, the flags -- become visible to the neighbour GPU only after the data
     __syncthreads();
     if (threadIdx.x == 0) {
+      __threadfence_system();
       const unsigned total = gridDim.x * gridDim.y * gridDim.z;
       if (atomicAdd(H.done, 1u) == total - 1) {
         *H.done = 0;  // next launch on this stream starts from zero
@@ -753,7 +758,7 @@ struct HaloUnpack {
 };
 __global__ void __launch_bounds__(256) k_unpack_halo(const __grid_constant__ HaloUnpack U, double* __restrict__ X, double2* __restrict__ R,
                                                       long long plane) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i0 = (long long)blockIdx.x * (256 * HALO_PER_THREAD) + threadIdx.x;
   const int j = blockIdx.y, side = blockIdx.z;
   if (U.flag[side] != nullptr) {
     if (threadIdx.x == 0) {
@@ -769,18 +774,22 @@ __global__ void __launch_bounds__(256) k_unpack_halo(const __grid_constant__ Hal
     }
     __syncthreads();
   }
-  if (i >= plane) return;
   const double* m = U.src[side];
-  if (j < 10) {
-    X[U.pop_dst[side][j] + i] = __ldcg(m + (long long)j * plane + i);
-  } else {
-    const double2 p = __ldcg(reinterpret_cast<const double2*>(m + 10 * plane) + i);
-    const double2 e = __ldcg(reinterpret_cast<const double2*>(m + 12 * plane) + i);
-    double2 b = R[U.r_bnd[side] + i], g = R[U.r_ghost[side] + i];
-    b.x += e.x; b.y += e.y;
-    g.x = p.x + g.x; g.y = p.y + g.y;
-    R[U.r_bnd[side] + i] = b;
-    R[U.r_ghost[side] + i] = g;
+#pragma unroll
+  for (int k = 0; k < HALO_PER_THREAD; ++k) {
+    const long long i = i0 + k * 256;
+    if (i >= plane) break;
+    if (j < 10) {
+      X[U.pop_dst[side][j] + i] = __ldcg(m + (long long)j * plane + i);
+    } else {
+      const double2 p = __ldcg(reinterpret_cast<const double2*>(m + 10 * plane) + i);
+      const double2 e = __ldcg(reinterpret_cast<const double2*>(m + 12 * plane) + i);
+      double2 b = R[U.r_bnd[side] + i], g = R[U.r_ghost[side] + i];
+      b.x += e.x; b.y += e.y;
+      g.x = p.x + g.x; g.y = p.y + g.y;
+      R[U.r_bnd[side] + i] = b;
+      R[U.r_ghost[side] + i] = g;
+    }
   }
 }
 

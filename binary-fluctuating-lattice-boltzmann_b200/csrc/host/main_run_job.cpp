@@ -8,7 +8,8 @@
 // File names follow main_run_job.cpp:150-202 (plot_file_dir, lbm_data_shshan_alpha0_.._xi_.._size.., f_checkpoint..).
 // Structure factors (FHDeX StructFact in the reference, main_run_job.cpp:299-310, 330, 342-349, 50-54): accumulated on the
 // GPU by libbflbm_sf.so (include/bflbm_sf.h) every out_SF_step steps inside the last plot_SF_window steps and written as
-// <plot_file_root>_SF<step> at the last step.  Out of scope: droplet radius fit.
+// <plot_file_root>_SF<step> at the last step.  Droplet runs print the centre of mass, the covariance eigenvalues and (if_print_radius)
+// the fitted (W, R) of the tanh profile at every plot step, all reduced on the GPU(s).
 #include <chrono>
 #include <cstdarg>
 #include <cmath>
@@ -74,6 +75,23 @@ int main(int argc, char** argv) {
     Lattice L(p, nx, ny, nz, R.device, R.ngpus, R.brick_lz);
     if (R.ngpus > 1) std::printf("%d GPUs: z-slabs, peer-to-peer ghost exchange\n", L.ngpus());
 
+    // ---- fluctuating run on the equilibrium reference state, main_run_job.cpp:214-236 + LBM_binary.H:12, 92-107 -------
+    if (noiseSwitch && R.use_ref_state) {
+      if (!L.handle()) throw std::runtime_error("use_ref_state needs ngpus = 1 (the centre of mass of the whole box enters every step)");
+      std::printf("Noise switch on\n");
+      const PlotfileData Er = read_plotfile(eq_name("rho")), Ep = read_plotfile(eq_name("phi")), Et = read_plotfile(eq_name("rhot"));
+      for (const PlotfileData* E : {&Er, &Ep, &Et})
+        if (E->nx != nx || E->ny != ny || E->nz != nz || E->ncomp != 1) throw std::runtime_error("equilibrium state does not match the box");
+      auto total = [](const std::vector<double>& v) { double s = 0.; for (double x : v) s += x; return s; };
+      std::printf("Mass rho_eq = %.15g\nMass phi_eq = %.15g\nMass rhot_eq = %.15g\n", total(Er.data), total(Ep.data), total(Et.data));
+      check(bflbm_set_reference_state(L.handle(), Er.data.data(), Ep.data.data(), Et.data.data()));
+      double c[3];
+      check(bflbm_get_reference_com(L.handle(), c));
+      std::printf("Center of Mass: (%g,%g,%g)\n", c[0], c[1], c[2]);
+    } else if (!noiseSwitch) {
+      std::printf("Noise switch off, calculating the equilibrium state solutions...\n");
+    }
+
     // ---- initialise, main_run_job.cpp:245-292 ------------------------------------------------------------
     if (R.if_continue_from_last_frame) {
       const double chk_temp = R.continueFromNonFluct ? 0. : R.kBT;
@@ -117,6 +135,7 @@ int main(int argc, char** argv) {
     }
 
     // ---- time loop, main_run_job.cpp:329-387 ------------------------------------------------------------------
+    std::vector<double> radius_frames;  // main_run_job.cpp:112, 368
     const auto t_loop = std::chrono::steady_clock::now();
     const int last = R.step_continue + R.nsteps;
     int step = R.step_continue;
@@ -149,6 +168,14 @@ int main(int argc, char** argv) {
           std::printf("Center of Mass: (%g,%g,%g)\n", c[0], c[1], c[2]);
           const auto ev = fittingDropletCovariance(L);  // LBM_hydrovs.H:258-335 (shape-mode diagnostics)
           std::printf("Covariance eigenvalues: (%.10g,%.10g,%.10g)\n", ev[0], ev[1], ev[2]);
+          if (R.if_print_radius) {  // main_run_job.cpp:364-368: fittingDropletParams(func_rho, 20, 0.01, 400, kappa, radius)
+            double wr[3];
+            int converged = 0;
+            mcheck(bflbm_multi_fit_droplet(L.multi(), 20, 0.01, 400, R.kappa, R.radius, 0.2, 0.2, 0.02, wr, &converged));
+            if (!converged) std::printf("statistical undulation %.2e out of bounds!\n", wr[2]);
+            std::printf("fitting parameters for equilibrium density rho: (W=%f, R=%f)\n", wr[0], wr[1]);
+            radius_frames.push_back(wr[1]);
+          }
         }
         if (step >= R.out_step && step != last) write_output(step);
       }

@@ -44,6 +44,8 @@ struct RunParameters {
   // LBM_d3q19.H:10, LBM_binary.H:17-30
   double kBT = 0., tau_f = 0.5, tau_g = 0.5, alpha0 = 4., alpha1 = 0., kappa = 4., rho_lo = 0., rho_hi = 1.;
   unsigned long long seed = 12345ull;
+  bool use_ref_state = false;  // the reference's USE_REF_STATE macro (LBM_binary.H:12, shipped commented out): noise amplitudes from
+                               // the equilibrium_* profiles of the kBT = 0 run, shifted with the centre of mass
   bool use_SC_pseudo = false;  // dead branch in the reference (LBM_binary.H:23); true is rejected
   double SC_ref_density = 1.;
 };
@@ -100,7 +102,7 @@ inline RunParameters parse_parameters(std::istream& in) {
   P_DBL(radius); P_BOOL(if_print_radius); P_DBL(init_frac); P_STR(root_path); P_INT(Ndigits); P_STR(plot_fields); P_INT(device); P_INT(ngpus); P_INT(brick_lz);
   P_DBL(kBT); P_DBL(tau_f); P_DBL(tau_g); P_DBL(alpha0); P_DBL(alpha1); P_DBL(kappa); P_DBL(rho_lo); P_DBL(rho_hi);
   take("seed", [&](const std::string& v) { P.seed = std::stoull(v); });
-  P_BOOL(use_SC_pseudo); P_DBL(SC_ref_density);
+  P_BOOL(use_ref_state); P_BOOL(use_SC_pseudo); P_DBL(SC_ref_density);
 #undef P_INT
 #undef P_DBL
 #undef P_BOOL

@@ -49,6 +49,29 @@ __device__ __forceinline__ long long nbr(const CellIdx& I, int i) {
   return I.zpl[1 + S * cz(i)] + I.yrow[1 + S * cy(i)] + I.xs[1 + S * cx(i)];
 }
 
+// USE_REF_STATE noise (LBM_binary.H:12, 92-107; whole-box lattices, thread-per-cell kernels): eq = [rho_eq | phi_eq | rhot_eq],
+// each nx*ny*nz doubles; shift = integer part of (centre of mass - com_ref), recomputed on the device after every step.
+struct RefState {
+  const double* eq;   // nullptr: the shipped behaviour (current densities)
+  const int* shift;
+};
+__device__ __forceinline__ bool ref_densities(const Geom& G, const RefState& RS, int x, int y, int zl, double (&d)[3]) {
+  if (RS.eq == nullptr) return false;
+  int xs = x - RS.shift[0], ys = y - RS.shift[1], zs = zl - RS.shift[2];
+  // single periodic wrap, like the reference (LBM_binary.H:97-102)
+  if (xs < 0) xs += G.nx;
+  if (xs > G.nx - 1) xs -= G.nx;
+  if (ys < 0) ys += G.ny;
+  if (ys > G.ny - 1) ys -= G.ny;
+  if (zs < 0) zs += G.nzl;
+  if (zs > G.nzl - 1) zs -= G.nzl;
+  const long long n = G.plane * G.nzl, c = (long long)zs * G.plane + (long long)ys * G.nx + xs;
+  d[0] = RS.eq[c];
+  d[1] = RS.eq[n + c];
+  d[2] = RS.eq[2 * n + c];
+  return true;
+}
+
 // pull the 19 post-stream populations of one species: f_i(x) = X_i(x - c_i)
 __device__ __forceinline__ void pull19(const double* __restrict__ Xs, const Geom& G, const CellIdx& I, double (&f)[Q]) {
 #pragma unroll
@@ -95,7 +118,8 @@ __device__ __forceinline__ void density_gradients(const double2* __restrict__ R,
 // the conserved moments are formed.  Two CTAs per SM (<= 128 registers): these kernels serve the small, latency-bound boxes.
 template <bool NOISE, bool RATE1>
 __global__ void __launch_bounds__(256, RATE1 ? 2 : 1) k_step_twopass(Geom G, DevParams P, long long step_arg, const long long* __restrict__ step_dev,
-                                                       const double* __restrict__ X, double* __restrict__ Xn, const double2* __restrict__ R) {
+                                                       const double* __restrict__ X, double* __restrict__ Xn, const double2* __restrict__ R,
+                                                       RefState RS) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zl = blockIdx.z;
   if (x >= G.nx || y >= G.ny) return;
   const long long step = step_arg + ((NOISE && step_dev != nullptr) ? *step_dev : 0ll);
@@ -111,7 +135,9 @@ __global__ void __launch_bounds__(256, RATE1 ? 2 : 1) k_step_twopass(Geom G, Dev
   CollideCtx C;
   float y3[3], yb[15];
   momentum_normals<NOISE>(nk, y3);
-  collide_prepare<NOISE>(P, grho, gphi, y3, mf, mg, C);
+  double ref3[3];
+  const bool use_ref = NOISE && ref_densities(G, RS, x, y, zl, ref3);
+  collide_prepare<NOISE>(P, grho, gphi, y3, mf, mg, C, use_ref ? ref3 : nullptr);
   const long long c = I.zpl[1] + I.yrow[1] + x;
   double p[Q];
   mode_normals<NOISE, 0>(nk, yb);
@@ -228,7 +254,7 @@ enum ObserveMode { OBS_POP = 0, OBS_HYDRO = 1, OBS_HBAR = 2, OBS_NOISE = 3, OBS_
 
 template <int MODE, bool NOISE>
 __global__ void __launch_bounds__(256) k_observe(Geom G, DevParams P, long long step, int zlo, const double* __restrict__ X,
-                                                  const double2* __restrict__ R, double* __restrict__ out) {
+                                                  const double2* __restrict__ R, double* __restrict__ out, RefState RS) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zc = blockIdx.z, zl = zlo + zc;
   if (x >= G.nx || y >= G.ny) return;
   const CellIdx I = cell_idx(G, x, y, zl);
@@ -275,10 +301,12 @@ __global__ void __launch_bounds__(256) k_observe(Geom G, DevParams P, long long 
 #pragma unroll
     for (int d = 0; d < 36; ++d) n[d] = NRM_BIAS_F;
   }
+  double ref3[3] = {rho, phi, rho + phi};
+  const bool use_ref = NOISE && ref_densities(G, RS, x, y, zl, ref3);
   if (MODE == OBS_NOISE) {
-    // fnoisevs / gnoisevs (LBM_binary.H:113-127)
-    const double aj = NOISE ? sqrt(P.amp_j * fabs(rho * phi / (rho + phi))) : 0.;
-    const double sf = NOISE ? sqrt(P.amp_s * fabs(rho)) : 0., sg = NOISE ? sqrt(P.amp_s * fabs(phi)) : 0.;
+    // fnoisevs / gnoisevs (LBM_binary.H:113-127; amplitudes from the reference state under USE_REF_STATE, :92-107)
+    const double aj = NOISE ? sqrt(P.amp_j * fabs(ref3[0] * ref3[1] / ref3[2])) : 0.;
+    const double sf = NOISE ? sqrt(P.amp_s * fabs(ref3[0])) : 0., sg = NOISE ? sqrt(P.amp_s * fabs(ref3[1])) : 0.;
     out[0 * oc + o] = 0.;
     out[(long long)Q * oc + o] = 0.;
 #pragma unroll
@@ -301,7 +329,7 @@ __global__ void __launch_bounds__(256) k_observe(Geom G, DevParams P, long long 
     const double jf[3] = {mf[1], mf[2], mf[3]}, jg[3] = {mg[1], mg[2], mg[3]};
     CellHydro H;
     double sq_rho, sq_phi;
-    cell_hydro<NOISE>(P, rho, phi, jf, jg, grho, gphi, n3, H, sq_rho, sq_phi);
+    cell_hydro<NOISE>(P, rho, phi, jf, jg, grho, gphi, n3, H, sq_rho, sq_phi, use_ref ? ref3 : nullptr);
     out[0 * oc + o] = rho;
     out[1 * oc + o] = phi;
     out[5 * oc + o] = rho + phi;
@@ -353,6 +381,70 @@ __global__ void __launch_bounds__(256) k_diag(Geom G, const double2* __restrict_
     const long long b = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
 #pragma unroll
     for (int k = 0; k < NDIAG; ++k) partial[b * NDIAG + k] = sh[k][0];
+  }
+}
+// Field terms of the droplet (W, R) fit (externlib.H:246-340: func_MfWn_mult, func_MfRn_mult): per-block partial sums of
+//   rho (R - r') sech^2((R - r') / s)   and   rho sech^2((R - r') / s),   r' = |r - r0|, unit-cube cell-centre coordinates,
+// plus (MINMAX) the block's min / max of rho for C0 = max rho - min rho (LBM_hydrovs.H:124-125).  partial: [block][4].
+__global__ void __launch_bounds__(256) k_fit_terms(Geom G, const double2* __restrict__ R, double inv_s, double Rn, double r0x, double r0y,
+                                                    double r0z, double* __restrict__ partial) {
+  __shared__ double sh[4][256];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, zl = blockIdx.z;
+  double v0 = 0., v1 = 0., mn = 1e300, mx = -1e300;
+  if (x < G.nx && y < G.ny) {
+    const double rho = R[(long long)(zl + 1) * G.plane + (long long)y * G.nx + x].x;
+    const double dx = (x + 0.5) / G.nx - r0x, dy = (y + 0.5) / G.ny - r0y, dz = (G.z0 + zl + 0.5) / G.nz_global - r0z;
+    const double dist = Rn - sqrt(dx * dx + dy * dy + dz * dz), a = dist * inv_s;
+    const double sech = fabs(a) < 710.4 ? 1. / cosh(a) : 0.;  // inv_acosh, externlib.H:23-30
+    v1 = rho * (sech * sech);
+    v0 = rho * (dist * sech * sech);
+    mn = mx = rho;
+  }
+  sh[0][tid] = v0; sh[1][tid] = v1; sh[2][tid] = mn; sh[3][tid] = mx;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) {
+      sh[0][tid] += sh[0][tid + s];
+      sh[1][tid] += sh[1][tid + s];
+      sh[2][tid] = fmin(sh[2][tid], sh[2][tid + s]);
+      sh[3][tid] = fmax(sh[3][tid], sh[3][tid + s]);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const long long b = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) partial[b * 4 + k] = sh[k][0];
+  }
+}
+
+// update_com for the reference-state noise (LBM_hydrovs.H:26-60, LBM_binary.H:586-588): block partials of k_diag summed in block
+// order by one thread block (deterministic), shift = (int)(com - com_ref) per axis (C truncation, like the reference's static_cast)
+__global__ void __launch_bounds__(256) k_com_shift(const double* __restrict__ partial, long long nblocks, double cx, double cy, double cz,
+                                                    int* __restrict__ shift) {
+  __shared__ double sh[4][256];
+  double v[4] = {0., 0., 0., 0.};
+  const int pick[4] = {0, 2, 3, 4};
+  // thread t sums blocks t, t + 256, ... in order; then a fixed tree
+  for (long long b = threadIdx.x; b < nblocks; b += 256)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] += partial[b * NDIAG + pick[k]];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] = v[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double m = sh[0][0];
+    shift[0] = (int)(sh[1][0] / m - cx);
+    shift[1] = (int)(sh[2][0] / m - cy);
+    shift[2] = (int)(sh[3][0] / m - cz);
   }
 }
 __global__ void k_count_nonfinite(const double* __restrict__ a, long long n, unsigned long long* __restrict__ cnt) {

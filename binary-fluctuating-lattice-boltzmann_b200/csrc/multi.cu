@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/bflbm.h"
+#include "droplet_fit.hpp"
 
 struct bflbm_multi {
   std::vector<bflbm_lattice*> L;
@@ -158,6 +159,47 @@ int bflbm_multi_droplet_covariance(bflbm_multi* m, double* com3, double* cov6, d
   return bflbm_covariance_from_moments(s, com3, cov6, eig3);
 }
 int bflbm_multi_center_of_mass(bflbm_multi* m, double* com3) { return bflbm_multi_droplet_covariance(m, com3, nullptr, nullptr); }
+
+// fittingDropletParams over all slabs: every flow step sums the slabs' field terms (bflbm_droplet_fit_terms)
+int bflbm_multi_fit_droplet(bflbm_multi* m, int step_window, double undul_ratio, int nstep, double W0, double R0, double eta_W, double eta_R,
+                            double dt, double* out3, int* converged) {
+  MCHECK(m);
+  if (!out3) return mfail(BFLBM_ERR_ARG, "null output");
+  if (m->whole) {
+    const int rc = bflbm_fit_droplet(m->L[0], step_window, undul_ratio, nstep, W0, R0, eta_W, eta_R, dt, out3, converged);
+    return rc ? mfail(rc, bflbm_last_error()) : 0;
+  }
+  if (nstep < 2 || step_window < 1 || step_window > nstep || !(W0 > 0.)) return mfail(BFLBM_ERR_ARG, "bad fit parameters");
+  double com[3];
+  int rc = bflbm_multi_center_of_mass(m, com);
+  if (rc) return rc;
+  const double r0[3] = {(com[0] + 0.5) / m->nx, (com[1] + 0.5) / m->ny, (com[2] + 0.5) / m->nz};
+  auto all = [m](double W, double R, const double* c, double* s4) {
+    s4[0] = s4[1] = 0.; s4[2] = 1e300; s4[3] = -1e300;
+    for (bflbm_lattice* l : m->L) {
+      double t[4];
+      const int e = bflbm_droplet_fit_terms(l, W, R, c, t);
+      if (e) return e;
+      s4[0] += t[0]; s4[1] += t[1]; s4[2] = std::min(s4[2], t[2]); s4[3] = std::max(s4[3], t[3]);
+    }
+    return 0;
+  };
+  double s4[4];
+  if ((rc = all(W0, R0, r0, s4))) return mfail(rc, bflbm_last_error());
+  const double range = s4[3] - s4[2];
+  bflbm::fit::FieldTerms terms = [&all](double W, double R, const double* c, double* sums) {
+    double t[4];
+    const int e = all(W, R, c, t);
+    sums[0] = t[0]; sums[1] = t[1];
+    return e;
+  };
+  bflbm::fit::Result res;
+  if ((rc = bflbm::fit::fit(terms, 1. / ((double)m->nx * m->ny * m->nz), r0, range, step_window, undul_ratio, nstep, W0, R0, eta_W, eta_R, dt, res)))
+    return mfail(rc, bflbm_last_error());
+  out3[0] = res.W; out3[1] = res.R; out3[2] = res.undulation;
+  if (converged) *converged = res.converged ? 1 : 0;
+  return 0;
+}
 
 int bflbm_multi_check_nan(bflbm_multi* m, long long* count) {
   MCHECK(m);

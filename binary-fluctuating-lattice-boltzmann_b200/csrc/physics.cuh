@@ -57,10 +57,12 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
 // when !NOISE.  sq_rho / sq_phi return sqrt|rho|, sqrt|phi| (for the stress-mode noise amplitudes of collide_species).
 // The three reciprocals (1/rho, 1/phi, 1/(rho+phi)) and three square roots the formulas need all come from three
 // reciprocal square roots: 1/x = sign(x) r^2, sqrt|x| = |x| r with r = rsqrt|x|  (each ~2 ulp; the bar is 1e-12).
+// ref3 != nullptr: USE_REF_STATE (LBM_binary.H:12, 92-107) -- the noise amplitudes are built from {rho, phi, rho_t} of the
+// equilibrium profile at the COM-shifted cell instead of the current densities (thread-per-cell kernels only).
 template <bool NOISE, bool FMA_NOISE = true>
 __device__ __forceinline__ void cell_hydro(const DevParams& P, double rho, double phi, const double (&jf)[3], const double (&jg)[3],
                                            const double (&grad_rho)[3], const double (&grad_phi)[3], const float (&y3)[3],
-                                           CellHydro& H, double& sq_rho, double& sq_phi) {
+                                           CellHydro& H, double& sq_rho, double& sq_phi, const double* ref3 = nullptr) {
   H.rho = rho;
   H.phi = phi;
   const bool has_f = fabs(rho) > (double)FLT_EPSILON, has_g = fabs(phi) > (double)FLT_EPSILON;
@@ -79,7 +81,12 @@ __device__ __forceinline__ void cell_hydro(const DevParams& P, double rho, doubl
   // n = 16 (D - 1.5):  xi = fma(16 amp, D, -24 amp)
   double amp16 = 0., ampb = 0.;
   if (NOISE) {
-    const double amp = P.sqrt_amp_j * (sq_rho * sq_phi) * rt;
+    double amp = P.sqrt_amp_j * (sq_rho * sq_phi) * rt;
+    if (ref3 != nullptr) {
+      sq_rho = sqrt(fabs(ref3[0]));
+      sq_phi = sqrt(fabs(ref3[1]));
+      amp = P.sqrt_amp_j * sqrt(fabs(ref3[0] * ref3[1] / ref3[2]));
+    }
     amp16 = NRM_SCALE * amp;
     ampb = -(NRM_SCALE * NRM_BIAS) * amp;
   }
@@ -122,9 +129,10 @@ struct CollideCtx {
 // counter, so the step kernel does it in the shadow of its population loads, before the first loaded value is needed.
 template <bool NOISE, bool FMA_NOISE = true>
 __device__ __forceinline__ void collide_prepare(const DevParams& P, const double (&grad_rho)[3], const double (&grad_phi)[3],
-                                                const float (&y3)[3], const double (&mf)[Q], const double (&mg)[Q], CollideCtx& C) {
+                                                const float (&y3)[3], const double (&mf)[Q], const double (&mg)[Q], CollideCtx& C,
+                                                const double* ref3 = nullptr) {
   const double jf[3] = {mf[1], mf[2], mf[3]}, jg[3] = {mg[1], mg[2], mg[3]};
-  cell_hydro<NOISE, FMA_NOISE>(P, mf[0], mg[0], jf, jg, grad_rho, grad_phi, y3, C.H, C.sq_rho, C.sq_phi);
+  cell_hydro<NOISE, FMA_NOISE>(P, mf[0], mg[0], jf, jg, grad_rho, grad_phi, y3, C.H, C.sq_rho, C.sq_phi, ref3);
 #pragma unroll
   for (int k = 0; k < 3; ++k) C.vb[k] = (C.H.rho * C.H.uf[k] + C.H.phi * C.H.ug[k]) * C.H.inv_tot;  // LBM_binary.H:471
 }

@@ -114,6 +114,12 @@ def load_library() -> ctypes.CDLL:
         "bflbm_droplet_covariance": (ip, [vp, vp, vp, vp]),
         "bflbm_debug_philox": (ip, [vp, vp, vp]),
         "bflbm_covariance_from_moments": (ip, [vp, vp, vp, vp]),
+        "bflbm_set_reference_state": (ip, [vp, vp, vp, vp]),
+        "bflbm_fit_droplet": (ip, [vp, ip, dp, ip, dp, dp, dp, dp, dp, vp, ctypes.POINTER(ip)]),
+        "bflbm_droplet_fit_terms": (ip, [vp, dp, dp, vp, vp]),
+        "bflbm_debug_fit_coefficients": (ip, [dp, dp, dp, dp, dp, dp, vp]),
+        "bflbm_multi_fit_droplet": (ip, [vp, ip, dp, ip, dp, dp, dp, dp, dp, vp, ctypes.POINTER(ip)]),
+        "bflbm_get_reference_com": (ip, [vp, vp]),
         "bflbm_init_from_global_populations": (ip, [vp, vp, vp]),
         "bflbm_get_populations_into_global": (ip, [vp, vp, vp]),
         "bflbm_get_hydrovars_into_global": (ip, [vp, vp]),
@@ -261,6 +267,20 @@ class Lattice:
         g = _host(g_global, shp, "g_global")
         _check(self.lib.bflbm_init_from_global_populations(self.h, f.ctypes.data, g.ctypes.data))
 
+    def set_reference_state(self, rho_eq=None, phi_eq=None, rhot_eq=None):
+        """USE_REF_STATE noise (LBM_binary.H:12, 92-107): amplitudes from these (nz, ny, nx) equilibrium profiles at the
+        COM-shifted cell; None switches back to the shipped behaviour."""
+        if rho_eq is None:
+            _check(self.lib.bflbm_set_reference_state(self.h, None, None, None))
+            return
+        a = [_host(v, self.shape, n) for v, n in ((rho_eq, "rho_eq"), (phi_eq, "phi_eq"), (rhot_eq, "rhot_eq"))]
+        _check(self.lib.bflbm_set_reference_state(self.h, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data))
+
+    def reference_com(self):
+        c = np.empty(3)
+        _check(self.lib.bflbm_get_reference_com(self.h, c.ctypes.data))
+        return c
+
     # -- peer mode (include/bflbm.h): the halo message goes straight into the neighbour's mailbox ----------------
     def peer_ipc_handle(self) -> bytes:
         buf = ctypes.create_string_buffer(64)
@@ -344,6 +364,14 @@ class Lattice:
         a, b = ctypes.c_double(), ctypes.c_double()
         _check(self.lib.bflbm_total_mass(self.h, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
+
+    def fit_droplet(self, W0, R0, step_window=20, undul_ratio=0.01, nstep=400, eta_W=0.2, eta_R=0.2, dt=0.02):
+        """fittingDropletParams (LBM_hydrovs.H:160-213, defaults of the call at main_run_job.cpp:365): (W, R, undulation, converged)."""
+        out = np.empty(3)
+        ok = ctypes.c_int()
+        _check(self.lib.bflbm_fit_droplet(self.h, int(step_window), float(undul_ratio), int(nstep), float(W0), float(R0), float(eta_W),
+                                          float(eta_R), float(dt), out.ctypes.data, ctypes.byref(ok)))
+        return float(out[0]), float(out[1]), float(out[2]), bool(ok.value)
 
     def check_nan(self) -> int:
         """Number of non-finite hydro values; raises BflbmError if any (the reference prints and exit(0)s,

@@ -98,6 +98,15 @@ int bflbm_init_from_populations(bflbm_lattice* h, const double* f, const double*
  * periodic neighbours' boundary planes (what FillBoundary would put in the first ghost layer). */
 int bflbm_init_from_populations_slab(bflbm_lattice* h, const double* f_ghosted, const double* g_ghosted);
 
+/* USE_REF_STATE (LBM_binary.H:12 -- shipped commented out -- and :92-107): the thermal-noise amplitudes are built from the
+ * equilibrium profiles rho_eq, phi_eq, rhot_eq (host, (nz, ny, nx) each: what main_run_job.cpp:216-221 loads from the
+ * equilibrium_* plotfiles of the kBT = 0 run) read at the cell shifted by the integer part of (centre of mass of rho now -
+ * centre of mass of rho_eq), which the library recomputes on the device after every step (update_com, LBM_binary.H:586-588).
+ * Whole-box lattices; switches the lattice to the thread-per-cell kernels.  NULL pointers switch back to the shipped
+ * behaviour (amplitudes from the current densities).  bflbm_get_reference_com: com_ref[0] of main_run_job.cpp:229-233. */
+int bflbm_set_reference_state(bflbm_lattice* h, const double* rho_eq, const double* phi_eq, const double* rhot_eq);
+int bflbm_get_reference_com(const bflbm_lattice* h, double* com3);
+
 /* LBM_timestep  LBM_binary.H:544-594, nsteps times.  Asynchronous on the lattice's stream.
  * For a slab lattice use bflbm_step_begin / halo exchange / bflbm_step_end instead. */
 int bflbm_step(bflbm_lattice* h, int nsteps);
@@ -146,6 +155,18 @@ int bflbm_second_moments(bflbm_lattice* h, double* sums10);
 int bflbm_droplet_covariance(bflbm_lattice* h, double* com3, double* cov6, double* eig3);
 /* The same from the ten sums (host arithmetic): add up bflbm_second_moments of all slabs of a box first. */
 int bflbm_covariance_from_moments(const double* sums10, double* com3, double* cov6, double* eig3);
+/* Droplet (W, R) fit: fittingDropletParams, LBM_hydrovs.H:160-213 (call site main_run_job.cpp:358-369, behind if_print_radius):
+ * rho ~ 1/2 (1 + tanh((R - |r - r0|) / sqrt(2W))) fitted by a damped gradient flow of `nstep` steps; the result is the mean of
+ * the last `step_window` steps, restarted with a smaller step (up to 10 times) while their spread exceeds undul_ratio.
+ * The reference's defaults: step_window 20, undul_ratio 0.01, nstep 400, W0 = kappa, R0 = radius, eta_W = eta_R = 0.2, dt = 0.02.
+ * Coordinates: unit cube.  out3 = {W, R, undulation}; *converged = 0 where the reference would throw.  The two lattice
+ * integrals of every flow step are device reductions (bflbm_droplet_fit_terms: local partial sums
+ * {sum rho (R - r') sech^2((R - r')/s), sum rho sech^2(..), min rho, max rho}, s = sqrt(2W), r0 in unit-cube coordinates). */
+int bflbm_fit_droplet(bflbm_lattice* h, int step_window, double undul_ratio, int nstep, double W0, double R0, double eta_W, double eta_R,
+                      double dt, double* out3, int* converged);
+int bflbm_droplet_fit_terms(bflbm_lattice* h, double W, double R, const double* r0, double* sums4);
+/* JRn_Rn, JWn_Rn, JRn_Wn, JWn_Wn, KWn, KRn of externlib.H:203-244, 342-366 (test hook; host arithmetic only) */
+int bflbm_debug_fit_coefficients(double W, double R, double eta_W, double eta_R, double dt, double C0, double* out6);
 /* sums of rho and phi over the local cells (Debug.H:35-72 / main_run_job.cpp:224-228) */
 int bflbm_total_mass(bflbm_lattice* h, double* mass_rho, double* mass_phi);
 /* MultiFabNANCheck  Debug.H:136-149: counts non-finite values in the 22 hydro fields.
@@ -221,6 +242,8 @@ int bflbm_multi_total_mass(bflbm_multi* m, double* mass_rho, double* mass_phi);
 int bflbm_multi_second_moments(bflbm_multi* m, double* sums10);
 int bflbm_multi_center_of_mass(bflbm_multi* m, double* com3);
 int bflbm_multi_droplet_covariance(bflbm_multi* m, double* com3, double* cov6, double* eig3);
+int bflbm_multi_fit_droplet(bflbm_multi* m, int step_window, double undul_ratio, int nstep, double W0, double R0, double eta_W, double eta_R,
+                            double dt, double* out3, int* converged);
 int bflbm_multi_check_nan(bflbm_multi* m, long long* count); /* also reports a timed-out halo wait */
 long long bflbm_multi_kernel_launches(const bflbm_multi* m);
 size_t bflbm_multi_device_bytes(const bflbm_multi* m);

@@ -50,6 +50,10 @@ typedef struct {
   double *hb;                  /* hydrovsbar [9][n]  */
   double *fn, *gn;             /* noise      [19][n] */
   const double* normals;       /* injected standard normals, 33 per cell, or NULL (= 0) */
+  /* USE_REF_STATE (LBM_binary.H:12, 92-107): noise amplitudes from the equilibrium profiles, shifted by the integer part of
+   * (centre of mass - com_ref); NULL = the shipped build (current densities) */
+  double *rho_eq, *phi_eq, *rhot_eq; /* [n] each */
+  double com_ref[3];
 } oracle_lattice;
 
 static void init_constants(void) {
@@ -280,17 +284,49 @@ static void hydrovars_density_all(oracle_lattice* L) {
 }
 
 /* LBM_binary.H:73-132 (non-USE_REF_STATE branch); tau_g_bar := tau_f_bar (:80) */
-static void thermal_noise_all(oracle_lattice* L) {
+/* update_com (LBM_hydrovs.H:26-60) of one [n] field: sum rho * index / sum rho, cells visited x fastest */
+static void center_of_mass(const oracle_lattice* L, const double* rho, double* com) {
+  double mass = 0., sx = 0., sy = 0., sz = 0.;
+  for (int k = 0; k < L->nz; ++k)
+    for (int j = 0; j < L->ny; ++j)
+      for (int i = 0; i < L->nx; ++i) {
+        const double r = rho[(size_t)i + (size_t)L->nx * ((size_t)j + (size_t)L->ny * (size_t)k)];
+        mass += r; sx += r * i; sy += r * j; sz += r * k;
+      }
+  com[0] = sx / mass; com[1] = sy / mass; com[2] = sz / mass;
+}
+
+/* relative: the caller is LBM_init / LBM_timestep (pos_com - com_ref[0], LBM_binary.H:586-588, 651-653); the analytic inits
+ * pass the absolute centre of mass (LBM_binary.H:623-625) */
+static void thermal_noise_all(oracle_lattice* L, int relative) {
   const oracle_params* p = &L->p;
   const size_t n = L->n;
   const double tfb = 1. / (p->tau_f + 0.5), tgb = tfb, tfb2 = tfb * tfb, tgb2 = tgb * tgb;
+  int shift[3] = {0, 0, 0};
+  if (L->rho_eq) {
+    double com[3];
+    center_of_mass(L, L->hb, com);
+    for (int d = 0; d < 3; ++d) shift[d] = (int)(relative ? com[d] - L->com_ref[d] : com[d]);
+  }
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static)
 #endif
   for (long c = 0; c < (long)n; ++c) {
     const double* N = L->normals ? L->normals + 33 * (size_t)c : NULL;
     int d = 0;
-    const double rho = L->hb[0 * n + c], phi = L->hb[1 * n + c], rhot = rho + phi;
+    double rho = L->hb[0 * n + c], phi = L->hb[1 * n + c], rhot = rho + phi;
+    if (L->rho_eq) { /* LBM_binary.H:92-107 */
+      int x = (int)(c % (size_t)L->nx), y = (int)((c / (size_t)L->nx) % (size_t)L->ny), z = (int)(c / ((size_t)L->nx * L->ny));
+      int xs = x - shift[0], ys = y - shift[1], zs = z - shift[2];
+      if (xs < 0) xs += L->nx;
+      if (xs > L->nx - 1) xs -= L->nx;
+      if (ys < 0) ys += L->ny;
+      if (ys > L->ny - 1) ys -= L->ny;
+      if (zs < 0) zs += L->nz;
+      if (zs > L->nz - 1) zs -= L->nz;
+      const size_t cs = cell_index(L, xs, ys, zs);
+      rho = L->rho_eq[cs]; phi = L->phi_eq[cs]; rhot = L->rhot_eq[cs];
+    }
     L->fn[0 * n + c] = 0.;
     L->gn[0 * n + c] = 0.;
     for (int a = 1; a <= 3; ++a) {
@@ -369,9 +405,9 @@ static void hydrovars_all(oracle_lattice* L) {
 }
 
 /* the tail every init and every step share: LBM_binary.H:583-592, 621-627 */
-static void refresh_derived(oracle_lattice* L) {
+static void refresh_derived(oracle_lattice* L, int relative) {
   hydrovars_density_all(L);
-  thermal_noise_all(L);
+  thermal_noise_all(L, relative);
   hydrovars_all(L);
 }
 
@@ -398,6 +434,7 @@ void* oracle_create(int nx, int ny, int nz) {
 void oracle_destroy(void* h) {
   oracle_lattice* L = (oracle_lattice*)h;
   free(L->f); free(L->g); free(L->fnew); free(L->gnew); free(L->h); free(L->hb); free(L->fn); free(L->gn);
+  free(L->rho_eq); free(L->phi_eq); free(L->rhot_eq);
   free(L);
 }
 void oracle_set_params(void* h, double kBT, double tau_f, double tau_g, double alpha0, double alpha1, double kappa,
@@ -405,6 +442,17 @@ void oracle_set_params(void* h, double kBT, double tau_f, double tau_g, double a
   oracle_lattice* L = (oracle_lattice*)h;
   L->p.kBT = kBT; L->p.tau_f = tau_f; L->p.tau_g = tau_g; L->p.alpha0 = alpha0; L->p.alpha1 = alpha1;
   L->p.kappa = kappa; L->p.rho_lo = rho_lo; L->p.rho_hi = rho_hi;
+}
+/* equilibrium profiles of the fluctuating run (main_run_job.cpp:216-236: load, com_ref = their centres of mass); NULL = off */
+void oracle_set_equilibrium(void* h, const double* rho_eq, const double* phi_eq, const double* rhot_eq) {
+  oracle_lattice* L = (oracle_lattice*)h;
+  free(L->rho_eq); free(L->phi_eq); free(L->rhot_eq);
+  L->rho_eq = L->phi_eq = L->rhot_eq = NULL;
+  if (!rho_eq) return;
+  const size_t n = L->n;
+  L->rho_eq = (double*)malloc(n * sizeof(double)); L->phi_eq = (double*)malloc(n * sizeof(double)); L->rhot_eq = (double*)malloc(n * sizeof(double));
+  memcpy(L->rho_eq, rho_eq, n * sizeof(double)); memcpy(L->phi_eq, phi_eq, n * sizeof(double)); memcpy(L->rhot_eq, rhot_eq, n * sizeof(double));
+  center_of_mass(L, L->rho_eq, L->com_ref);
 }
 /* 33 standard normals per cell (cell-major, reference draw order) used by the NEXT noise generation; NULL = zeros */
 void oracle_set_normals(void* h, const double* normals) { ((oracle_lattice*)h)->normals = normals; }
@@ -420,7 +468,7 @@ void oracle_init_mixture(void* h) {
   oracle_lattice* L = (oracle_lattice*)h;
   const double C1 = 0.5, C2 = 0.5;
   for (size_t c = 0; c < L->n; ++c) fill_from_density(L, c, 2. * C1, 2. * C2);
-  refresh_derived(L);
+  refresh_derived(L, 0);
 }
 /* LBM_binary.H:663-695 */
 void oracle_init_stripe(void* h, double frac) {
@@ -434,7 +482,7 @@ void oracle_init_stripe(void* h, double frac) {
     for (int y = 0; y < L->ny; ++y)
       for (int x = 0; x < L->nx; ++x) fill_from_density(L, cell_index(L, x, y, z), rho, rho_t - rho);
   }
-  refresh_derived(L);
+  refresh_derived(L, 0);
 }
 /* LBM_binary.H:698-742; rz uses box[0] and integer division (:725) */
 void oracle_init_droplet(void* h, double r_frac) {
@@ -453,21 +501,21 @@ void oracle_init_droplet(void* h, double r_frac) {
         const double rho = (p->rho_hi - p->rho_lo) * (1. + tanh((R - r) / sqrt(p->kappa))) / 2. + p->rho_lo;
         fill_from_density(L, cell_index(L, x, y, z), rho, rho_tot - rho);
       }
-  refresh_derived(L);
+  refresh_derived(L, 0);
 }
 /* restart entry, LBM_binary.H:631-661 */
 void oracle_init_from_populations(void* h, const double* f0, const double* g0) {
   oracle_lattice* L = (oracle_lattice*)h;
   memcpy(L->f, f0, NVEL * L->n * sizeof(double));
   memcpy(L->g, g0, NVEL * L->n * sizeof(double));
-  refresh_derived(L);
+  refresh_derived(L, 1);
 }
 /* LBM_timestep, LBM_binary.H:544-594 */
 void oracle_step(void* h, int nsteps) {
   oracle_lattice* L = (oracle_lattice*)h;
   for (int s = 0; s < nsteps; ++s) {
     collide_stream_all(L);
-    refresh_derived(L);
+    refresh_derived(L, 1);
   }
 }
 void oracle_get_populations(void* h, double* f, double* g) {

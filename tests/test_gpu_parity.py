@@ -200,6 +200,59 @@ def test_fluctuating_step_with_injected_normals(bflbm, oracle_mod, algo, tau):
         assert lat.step_count == 17 + 4
 
 
+@pytest.mark.parametrize("tau", [(0.5, 0.5), (0.7, 0.6)])
+def test_reference_state_noise_with_injected_normals(bflbm, oracle_mod, tau):
+    """USE_REF_STATE (LBM_binary.H:12, 92-107): noise amplitudes from the equilibrium profiles at the COM-shifted cell.  The CPU port
+    of that branch is pinned bit for bit to the reference headers built with -DUSE_REF_STATE (tests/test_oracle.py); here the
+    CUDA path is driven next to it with the GPU's normals.  The equilibrium state is displaced by (2, -1, 3) cells, so the integer
+    shift the device recomputes after every step (update_com) is non-zero in every direction."""
+    shape = (10, 12, 14)
+    prm = dict(kBT=2e-5, tau_f=tau[0], tau_g=tau[1], alpha0=1.5, alpha1=0.0, kappa=0.1, rho_lo=0.1, rho_hi=3.0)
+    f, g = oracle_mod.droplet_populations(*shape, 0.3, 0.1, 0.1, 3.0)
+    P0 = oracle_mod.PortOracle(*shape)
+    P0.set_params(**dict(prm, kBT=0.0))
+    P0.init_from_populations(f, g)
+    P0.step(5)
+    hb = P0.hydrovars_bar()
+    rho_eq, phi_eq = (np.roll(hb[k], (3, -1, 2), axis=(0, 1, 2)).copy() for k in (0, 1))
+    # a smooth asymmetric modulation moves the centre of mass by a NON-integer amount: the shift is an integer truncation of
+    # (com - com_ref), which must not sit on a rounding knife edge
+    zz, yy, xx = np.meshgrid(*(np.arange(n) for n in shape[::-1]), indexing="ij")
+    rho_eq *= 1.0 + 0.3 * np.cos(2 * np.pi * (xx + 0.3) / shape[0]) * np.cos(2 * np.pi * (yy - 1.1) / shape[1]) * np.sin(2 * np.pi * (zz + 0.7) / shape[2])
+    O = oracle_mod.PortOracle(*shape)
+    O.set_params(**prm)
+    O.set_equilibrium(rho_eq, phi_eq, rho_eq + phi_eq)
+    with bflbm.Lattice(*shape[:3], params=bflbm.Params(**prm, seed=77)) as lat:
+        lat.set_reference_state(rho_eq, phi_eq, rho_eq + phi_eq)
+        com = np.array([(rho_eq * c).sum() / rho_eq.sum() for c in np.meshgrid(*(np.arange(n) for n in shape[::-1]), indexing="ij")])[::-1]
+        assert np.allclose(lat.reference_com(), com, rtol=1e-12)
+        lat.init_from_populations(f, g)
+        O.set_normals(lat.normals())
+        O.init_from_populations(f, g)
+        fn, gn = lat.noise()
+        fo, go = O.noise()
+        assert rel_err(fn, fo) < TOL and rel_err(gn, go) < TOL, "reference-state noise amplitudes after the restart"
+        assert_hydro_close(lat.hydrovars(), O.hydrovars(), TOL, "ref-state restart")
+        for s in range(4):
+            lat.step(1)
+            O.set_normals(lat.normals())
+            O.step(1)
+            fn, gn = lat.noise()
+            fo, go = O.noise()
+            assert rel_err(fn, fo) < 10 * TOL and rel_err(gn, go) < 10 * TOL, f"noise after step {s + 1}"
+            assert_hydro_close(lat.hydrovars(), O.hydrovars(), 10 * TOL, f"ref-state step {s + 1}")
+        lat.step(20)  # graph-replayed chunk with the device-side centre of mass in the loop
+        assert lat.check_nan() == 0
+        # switching the reference state off gives the shipped noise (current densities) again
+        lat.set_reference_state(None)
+        O.set_equilibrium(None, None, None)
+        f1, g1 = lat.populations()
+        lat.init_from_populations(f1, g1)
+        O.set_normals(lat.normals())
+        O.init_from_populations(f1, g1)
+        assert rel_err(lat.noise()[0], O.noise()[0]) < TOL
+
+
 def test_normals_are_standard_and_keyed(bflbm):
     """Counter-based noise: N(0,1) moments, independence across draws/cells/steps, reproducibility, seed/step keys."""
     prm = dict(kBT=1e-5)

@@ -112,20 +112,27 @@ def test_capillary_wave_spectrum(bflbm, oracle_mod):
     C = ref["case"]
     C["shape"] = tuple(C["shape"])
     f, g = oracle_mod.stripe_populations(*C["shape"], C["frac"], C["params"]["kappa"], C["rho_lo"], C["rho_hi"])
-    prm = dict(C["params"], kBT=0.0, rho_lo=C["rho_lo"], rho_hi=C["rho_hi"], seed=271828)
-    with bflbm.Lattice(*C["shape"], params=bflbm.Params(**prm)) as lat:
-        lat.init_from_populations(f, g)
-        got = G.run_capillary(lat.step, lambda: lat.hydrovars_bar()[0], lambda kbt: lat.set_params(kBT=kbt), C)
+    # the same ensemble as the reference side: `replicas` independent runs (own seed each), spectra averaged
+    nrep = int(ref.get("replicas", 1))
+    runs = []
+    for r in range(nrep):
+        prm = dict(C["params"], kBT=0.0, rho_lo=C["rho_lo"], rho_hi=C["rho_hi"], seed=271828 + 7919 * r)
+        with bflbm.Lattice(*C["shape"], params=bflbm.Params(**prm)) as lat:
+            lat.init_from_populations(f, g)
+            runs.append(G.run_capillary(lat.step, lambda: lat.hydrovars_bar()[0], lambda kbt: lat.set_params(kBT=kbt), C))
+    got = G.combine_capillary(runs, C)
     _record("capillary", got)
     # deterministic relaxation: same interface position as the reference code (free-running 3000 steps)
     assert abs(got["h_det"] - ref["h_det"]) < 1e-8 * ref["h_det"], (got["h_det"], ref["h_det"])
-    assert abs(got["h_mean"] - ref["h_mean"]) < 0.05, (got["h_mean"], ref["h_mean"])
+    assert abs(got["h_mean"] - ref["h_mean"]) < 0.02, (got["h_mean"], ref["h_mean"])
     k, p, rp = np.array(got["k"]), np.array(got["hk2"]), np.array(ref["hk2"])
-    low = k <= 1.2  # the capillary regime (k * interface width < 1); ~1500 frames, modes decorrelate within a few frames
+    low = k <= 1.2  # the capillary regime (k * interface width < 1)
     ratio = p[low] / rp[low]
-    assert np.abs(ratio - 1).max() < 0.25, f"<|h_k|^2> GPU / reference per mode: {ratio}"
-    assert abs(np.mean(ratio) - 1) < 0.10, f"mean spectrum ratio {np.mean(ratio):.3f}"
-    assert abs(got["gamma_lowk"] / ref["gamma_lowk"] - 1) < 0.10, (got["gamma_lowk"], ref["gamma_lowk"])
+    # 16 x 1500 frames on each side: ~3 % per mode and side (the slowest modes decorrelate over tens of frames)
+    tol_mode, tol_mean = (0.10, 0.04) if nrep >= 8 else (0.25, 0.10)
+    assert np.abs(ratio - 1).max() < tol_mode, f"<|h_k|^2> GPU / reference per mode: {ratio}"
+    assert abs(np.mean(ratio) - 1) < tol_mean, f"mean spectrum ratio {np.mean(ratio):.3f}"
+    assert abs(got["gamma_lowk"] / ref["gamma_lowk"] - 1) < tol_mean + 0.01, (got["gamma_lowk"], ref["gamma_lowk"])
     # k^-2 law of the capillary regime: k^2 <|h_k|^2> flat within 35 % over the three lowest modes
     flat = (k ** 2 * p)[:3]
     assert flat.max() / flat.min() < 1.35, flat
@@ -144,13 +151,18 @@ def test_droplet_shape_mode_variance(bflbm, oracle_mod):
     C = ref["case"]
     C["shape"] = tuple(C["shape"])
     f, g = oracle_mod.droplet_populations(*C["shape"], C["radius"], C["params"]["kappa"], C["rho_lo"], C["rho_hi"])
-    prm = dict(C["params"], kBT=0.0, rho_lo=C["rho_lo"], rho_hi=C["rho_hi"], seed=161803)
-    with bflbm.Lattice(*C["shape"], params=bflbm.Params(**prm)) as lat:
-        lat.init_from_populations(f, g)
-        got = G.run_droplet(lat.step, lambda: lat.hydrovars_bar()[0], lambda kbt: lat.set_params(kBT=kbt), C)
+    nrep = int(ref.get("replicas", 1))
+    runs = []
+    for r in range(nrep):
+        prm = dict(C["params"], kBT=0.0, rho_lo=C["rho_lo"], rho_hi=C["rho_hi"], seed=161803 + 7919 * r)
+        with bflbm.Lattice(*C["shape"], params=bflbm.Params(**prm)) as lat:
+            lat.init_from_populations(f, g)
+            runs.append(G.run_droplet(lat.step, lambda: lat.hydrovars_bar()[0], lambda kbt: lat.set_params(kBT=kbt), C))
+    got = G.combine_droplet(runs)
     _record("droplet", got)
     assert np.allclose(got["axes_det"], ref["axes_det"], rtol=1e-9, atol=0), "deterministic relaxation: same droplet shape"
-    assert np.abs(np.array(got["axes_mean"]) - np.array(ref["axes_mean"])).max() < 2e-3
+    assert np.abs(np.array(got["axes_mean"]) - np.array(ref["axes_mean"])).max() < (1e-3 if nrep >= 8 else 2e-3)
+    lo, hi = (0.75, 1.25) if nrep >= 8 else (0.6, 1.6)  # 16 x 600 frames per side: ~6 % each
     for key in ("sum_plus", "sum_minus"):
         ratio = got[key] / ref[key]
-        assert 0.6 < ratio < 1.6, f"{key}: GPU {got[key]:.3e} vs reference {ref[key]:.3e} (ratio {ratio:.2f})"
+        assert lo < ratio < hi, f"{key}: GPU {got[key]:.3e} vs reference {ref[key]:.3e} (ratio {ratio:.2f})"

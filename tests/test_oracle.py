@@ -156,3 +156,55 @@ def test_tau_half_forgets_nonconserved_moments(oracle_mod):
     A = oracle_mod.PortOracle(6, 6, 6); A.set_params(**P.params); A.init_from_populations(f, g); A.step(1)
     B = oracle_mod.PortOracle(6, 6, 6); B.set_params(**P.params); B.init_from_populations(f2, g); B.step(1)
     assert np.abs(A.populations()[0] - B.populations()[0]).max() < 1e-15
+
+
+def test_port_reference_state_noise_matches_ref_build_bitwise(oracle_mod):
+    """the reference headers compiled with -DUSE_REF_STATE (the macro LBM_binary.H:12 ships commented out) draw
+    the noise amplitudes from the COM-shifted equilibrium profiles (:92-107, com_ref from main_run_job.cpp:229-233).  The C port's
+    restatement of that branch is pinned bit for bit, with injected normals, general relaxation times and an equilibrium state
+    displaced by (2, -1, 3) cells so that every component of the integer shift is non-zero."""
+    if not oracle_mod.RefOracle.available(ref_state=True):
+        pytest.skip("oracle/_ref/libbflbm_ref_refstate.so not built (needs /root/reference)")
+    shape = (10, 12, 14)
+    rng = np.random.default_rng(5)
+    prm = dict(kBT=2e-5, tau_f=0.7, tau_g=0.6, alpha0=1.5, alpha1=0.0, kappa=0.1)
+    f, g = oracle_mod.droplet_populations(*shape, 0.3, 0.1, 0.1, 3.0)
+    P0 = oracle_mod.PortOracle(*shape)
+    P0.set_params(**dict(prm, kBT=0.0), rho_lo=0.1, rho_hi=3.0)
+    P0.init_from_populations(f, g)
+    P0.step(5)
+    hb = P0.hydrovars_bar()
+    rho_eq, phi_eq = (np.roll(hb[k], (3, -1, 2), axis=(0, 1, 2)).copy() for k in (0, 1))
+    # a smooth asymmetric modulation moves the centre of mass by a NON-integer amount: the shift is an integer truncation of
+    # (com - com_ref), which must not sit on a rounding knife edge
+    zz, yy, xx = np.meshgrid(*(np.arange(n) for n in shape[::-1]), indexing="ij")
+    rho_eq *= 1.0 + 0.3 * np.cos(2 * np.pi * (xx + 0.3) / shape[0]) * np.cos(2 * np.pi * (yy - 1.1) / shape[1]) * np.sin(2 * np.pi * (zz + 0.7) / shape[2])
+    R = oracle_mod.RefOracle(*shape, ref_state=True)
+    assert R.uses_ref_state()
+    R.set_params(**prm)
+    R.set_equilibrium(rho_eq, phi_eq, rho_eq + phi_eq)
+    P = oracle_mod.PortOracle(*shape)
+    P.set_params(**prm, rho_lo=0.1, rho_hi=3.0)
+    P.set_equilibrium(rho_eq, phi_eq, rho_eq + phi_eq)
+    n = rng.standard_normal(shape[::-1] + (33,))
+    R.set_normals(n)
+    P.set_normals(n)
+    R.init_from_populations(f, g)
+    P.init_from_populations(f, g)
+    assert np.array_equal(R.noise()[0], P.noise()[0]) and np.array_equal(R.hydrovars(), P.hydrovars())
+    for _ in range(4):
+        n = rng.standard_normal(shape[::-1] + (33,))
+        R.set_normals(n)
+        P.set_normals(n)
+        R.step(1)
+        P.step(1)
+        assert np.array_equal(R.noise()[0], P.noise()[0]) and np.array_equal(R.noise()[1], P.noise()[1])
+        assert np.array_equal(R.hydrovars(), P.hydrovars()) and np.array_equal(R.populations()[1], P.populations()[1])
+    # and it is a different noise field from the shipped build's (current densities)
+    Q = oracle_mod.PortOracle(*shape)
+    Q.set_params(**prm, rho_lo=0.1, rho_hi=3.0)
+    Q.set_normals(n)
+    Q.init_from_populations(f, g)
+    P.set_normals(n)
+    P.init_from_populations(f, g)
+    assert np.abs(Q.noise()[0] - P.noise()[0]).max() > 1e-3
