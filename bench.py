@@ -111,6 +111,30 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are allocated (first touch puts
+    their pages on that node).  Round 1: eight ranks uploading 40.8 GB each from one node's memory fell from 48 to 18 GB/s per GPU.
+    Best effort; returns a description for the JSON line."""
+    try:
+        bus = subprocess.run(["nvidia-smi", f"--id={index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True,
+                             timeout=10).stdout.strip().lower()
+        bus = bus[4:] if len(bus) > 12 else bus  # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "single NUMA node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"rank bound to NUMA node {node} ({len(cpus)} cpus) of GPU {index}"
+        return "no usable cpus on the GPU's node"
+    except Exception as e:  # noqa
+        return f"not bound ({type(e).__name__})"
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -208,6 +232,7 @@ def run_b200(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the b200 arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
@@ -339,7 +364,7 @@ def run_b200(a):
                        "nonfinite_after_run": nan_count, "mass_rho": mass[0], "mass_phi": mass[1], "cells": cells,
                        "halo": None if world == 1 else ("peer-to-peer stores into CUDA-IPC-mapped mailboxes, device-side flags (no collective per step)"
                                                         if halo == "peer" else "NCCL send/recv (torch.distributed)"),
-                       "slab_parity": slab_parity},
+                       "slab_parity": slab_parity, "numa": numa},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         }
         print(json.dumps(line), flush=True)

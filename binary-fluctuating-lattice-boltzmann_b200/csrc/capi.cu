@@ -134,7 +134,7 @@ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 template <int NT, class Fn>
 cudaError_t for_each_fused(Fn fn) {
   cudaError_t e = cudaSuccess;
-#define BFLBM_EACH(N, R1, FU) if (e == cudaSuccess) e = fn((const void*)k_step_fused<N, R1, FU, NT>, R1)
+#define BFLBM_EACH(N, R1, FU) if (e == cudaSuccess) e = fn((const void*)k_step_fused<N, R1, FU, NT>, R1, N)
   BFLBM_EACH(false, false, false); BFLBM_EACH(false, false, true); BFLBM_EACH(false, true, false); BFLBM_EACH(false, true, true);
   BFLBM_EACH(true, false, false);  BFLBM_EACH(true, false, true);  BFLBM_EACH(true, true, false);  BFLBM_EACH(true, true, true);
 #undef BFLBM_EACH
@@ -144,12 +144,12 @@ cudaError_t for_each_fused(Fn fn) {
 // set once to the largest need over every brick shape make_brick_grid can produce (tx = 8, 16, 32): lattices of different
 // shape or tau can then coexist.
 template <int NT>
-size_t fused_smem_max(bool rate1) {
+size_t fused_smem_max(bool rate1, bool noise) {
   size_t m = 0;
   for (int tx = 8; tx <= 32; tx <<= 1) {
     BrickGrid B{};
     B.tx = tx; B.ty = NT / tx; B.ex = B.tx + 2; B.ey = B.ty + 2; B.pl = B.ex * B.ey;
-    m = std::max(m, fused_smem_bytes(B, rate1));
+    m = std::max(m, fused_smem_bytes(B, rate1, noise));
   }
   return m;
 }
@@ -158,18 +158,18 @@ cudaError_t set_fused_smem() {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess || (dev < 64 && done[dev])) return e;
-  e = for_each_fused<128>([&](const void* k, bool rate1) {
-    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_max<128>(rate1));
+  e = for_each_fused<128>([&](const void* k, bool rate1, bool noise) {
+    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_max<128>(rate1, noise));
   });
   if (e == cudaSuccess)
-    e = for_each_fused<256>([&](const void* k, bool rate1) {
-      return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_max<256>(rate1));
+    e = for_each_fused<256>([&](const void* k, bool rate1, bool noise) {
+      return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_max<256>(rate1, noise));
     });
   // BFLBM_CARVEOUT=<percent of the SM's shared memory>: experiment knob (the driver otherwise sizes the carve-out to the
   // resident CTAs' need; what is left of the 256 KB is L1)
   if (const char* cv = getenv("BFLBM_CARVEOUT")) {
     const int pct = atoi(cv);
-    auto setc = [&](const void* k, bool) { return cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct); };
+    auto setc = [&](const void* k, bool, bool) { return cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct); };
     if (e == cudaSuccess) e = for_each_fused<128>(setc);
     if (e == cudaSuccess) e = for_each_fused<256>(setc);
   }
@@ -436,9 +436,9 @@ int launch_fused_v(bflbm_lattice* h, int rows, cudaStream_t st) {
   const long long step = h->in_graph_capture ? (long long)h->graph_step_off : h->step;
   const long long* sdev = h->in_graph_capture ? h->d_step : nullptr;
   if (B.tx * B.ty == 128)
-    k_step_fused<NOISE, R1, FU, 128><<<grid, block, fused_smem_bytes(B, R1), st>>>(h->G, B, h->dp, step, sdev, XB, h->R, Ein, Eout, bz0, two_ends);
+    k_step_fused<NOISE, R1, FU, 128><<<grid, block, fused_smem_bytes(B, R1, NOISE), st>>>(h->G, B, h->dp, step, sdev, XB, h->R, Ein, Eout, bz0, two_ends);
   else
-    k_step_fused<NOISE, R1, FU, 256><<<grid, block, fused_smem_bytes(B, R1), st>>>(h->G, B, h->dp, step, sdev, XB, h->R, Ein, Eout, bz0, two_ends);
+    k_step_fused<NOISE, R1, FU, 256><<<grid, block, fused_smem_bytes(B, R1, NOISE), st>>>(h->G, B, h->dp, step, sdev, XB, h->R, Ein, Eout, bz0, two_ends);
   ++h->launches;
   CU(cudaGetLastError());
   return 0;
@@ -1262,6 +1262,9 @@ int bflbm_get_hydrovars_bar_into_global(bflbm_lattice* h, double* g9) { return o
 int bflbm_get_hydrovars(bflbm_lattice* h, double* out22) { return observe<OBS_HYDRO>(h, BFLBM_NHYDRO, out22, false, false); }
 int bflbm_get_hydrovars_bar(bflbm_lattice* h, double* out9) { return observe<OBS_HBAR>(h, BFLBM_NHYDRO_BAR, out9, false, false); }
 int bflbm_get_hydrovars_device(bflbm_lattice* h, double* o) { return observe<OBS_HYDRO>(h, BFLBM_NHYDRO, o, true, false); }
+// device array of the WHOLE box (may live on another GPU of this process: unified addressing makes the copy a peer copy)
+int bflbm_get_hydrovars_device_into_global(bflbm_lattice* h, double* g22) { return observe<OBS_HYDRO>(h, BFLBM_NHYDRO, g22, true, false, true); }
+int bflbm_get_device(const bflbm_lattice* h) { return h ? h->device : -1; }
 int bflbm_get_hydrovars_bar_device(bflbm_lattice* h, double* o) { return observe<OBS_HBAR>(h, BFLBM_NHYDRO_BAR, o, true, false); }
 int bflbm_get_noise(bflbm_lattice* h, double* fn, double* gn) { return observe_pair<OBS_NOISE>(h, fn, gn, false); }
 int bflbm_get_noise_into_global(bflbm_lattice* h, double* fn, double* gn) { return observe_pair<OBS_NOISE>(h, fn, gn, true); }
@@ -1475,6 +1478,38 @@ int bflbm_debug_philox(const unsigned int ctr[4], const unsigned int key[2], uns
   cudaFree(d);
   if (e != cudaSuccess) return fail(BFLBM_ERR_CUDA, "philox test: %s", cudaGetErrorString(e));
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+  return 0;
+}
+
+int bflbm_debug_normal_statistics(unsigned long long seed, long long ncells, long long step0, int nsteps, int nbins, double lo, double hi,
+                                  unsigned long long* hist, unsigned long long* joint, double* moments4) {
+  if (!hist || !joint || !moments4 || ncells < 1 || nsteps < 1 || nbins < 1 || nbins > 4096 || !(hi > lo)) return fail(BFLBM_ERR_ARG, "bad argument");
+  // a thread adds at most 33 * nsteps * (cells per thread) to one 32-bit shared counter per launch: bound the work per launch
+  const size_t nh = (size_t)nbins + 2, nj = (size_t)NORMAL_JOINT_BINS * NORMAL_JOINT_BINS;
+  unsigned long long *dh = nullptr, *dj = nullptr;
+  double* dm = nullptr;
+  CU(cudaMalloc((void**)&dh, nh * sizeof(unsigned long long)));
+  CU(cudaMalloc((void**)&dj, nj * sizeof(unsigned long long)));
+  CU(cudaMalloc((void**)&dm, 4 * sizeof(double)));
+  CU(cudaMemset(dh, 0, nh * sizeof(unsigned long long)));
+  CU(cudaMemset(dj, 0, nj * sizeof(unsigned long long)));
+  CU(cudaMemset(dm, 0, 4 * sizeof(double)));
+  const PhiloxKeys K = philox_key_schedule(seed);
+  const size_t smem = (nh + nj) * sizeof(unsigned int);
+  // per launch: 148 * 8 CTAs x 256 threads, each thread <= 16 cells x <= 64 steps x 33 draws = 33 792 increments (< 2^32 per CTA counter)
+  const long long chunk_cells = 148ll * 8 * 256 * 16;
+  for (long long c0 = 0; c0 < ncells; c0 += chunk_cells)
+    for (int s0 = 0; s0 < nsteps; s0 += 64) {
+      const long long nc = std::min(chunk_cells, ncells - c0);
+      k_normal_stats<<<148 * 8, 256, smem>>>(K, nc, step0 + s0 + (c0 << 20), std::min(64, nsteps - s0), nbins, lo, hi, dh, dj, dm);
+      CU(cudaGetLastError());
+    }
+  // (cells of later chunks are decorrelated from earlier ones through the step word of the counter instead of the cell word:
+  //  the kernel numbers its cells from 0)
+  CU(cudaMemcpy(hist, dh, nh * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(joint, dj, nj * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(moments4, dm, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(dh); cudaFree(dj); cudaFree(dm);
   return 0;
 }
 

@@ -86,9 +86,10 @@ inline BrickGrid make_brick_grid(const Geom& G, int lz_request = 0, int nthreads
 }
 inline size_t brick_doubles2(const BrickGrid& B) { return (size_t)B.brick * B.bx * B.by * B.bz; }
 constexpr int FIX_SLOTS = 200;  // extra contributions of one extended plane: 2*(ex + ey) + 4*12 - ... <= 192 for ex*ey <= 2*NT
-inline size_t fused_smem_bytes(const BrickGrid& B, bool rate1) {
+inline size_t fused_smem_bytes(const BrickGrid& B, bool rate1, bool noise) {
   return (size_t)7 * B.pl * sizeof(double2) + (size_t)B.pl * sizeof(int4) + (size_t)FIX_SLOTS * sizeof(double2) +
-         (rate1 ? 0 : (size_t)((BFLBM_G_MOMENT_SPACE ? 15 : BFLBM_PARK_G) + BFLBM_PARK_F) * B.tx * B.ty * sizeof(double));
+         (rate1 ? 0 : (size_t)((BFLBM_G_MOMENT_SPACE ? 15 : BFLBM_PARK_G) + BFLBM_PARK_F) * B.tx * B.ty * sizeof(double)) +
+         ((BFLBM_TRIG_TABLE && noise) ? (size_t)1024 * sizeof(float2) : 0);
 }
 // fold-in-staging (the step kernel sums the brick contributions itself) needs every cell to lie in at most
 // 2 bricks per axis, i.e. no brick of width 1
@@ -204,6 +205,14 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
   int4* Tab = reinterpret_cast<int4*>(smem + 7 * B.pl);     // [ey][ex] fold table: 3 extra sources + meta per entry
   double2* Fix = smem + 8 * B.pl;                           // [FIX_SLOTS] landing slots of the extra contributions
   double* So = reinterpret_cast<double*>(Fix + FIX_SLOTS);  // [19][NT] incoming populations of species g (!RATE1)
+  // (cos, sin) of the 1024 Box-Muller angles (philox.cuh), behind everything else
+  const float2* Trig = nullptr;
+  constexpr bool TAB = NOISE && BFLBM_TRIG_TABLE;
+  if (TAB) {
+    float2* t = reinterpret_cast<float2*>(So + (RATE1 ? 0 : ((BFLBM_G_MOMENT_SPACE ? 15 : BFLBM_PARK_G) + BFLBM_PARK_F) * NT));
+    fill_trig_table(t, threadIdx.y * B.tx + threadIdx.x, NT);
+    Trig = t;
+  }
   // rate-1 kernels make all 33 normals in the load shadow; the general kernels (19 more live doubles) make g's 15 late
   constexpr int PARK_F = BFLBM_PARK_F, PARK_G = BFLBM_PARK_G;
   constexpr bool FMA_NOISE = RATE1 || BFLBM_GENERAL_FMA_NOISE;  // how the noise is applied (philox.cuh)
@@ -404,10 +413,10 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
           constexpr bool Y3_LATE = !RATE1 && BFLBM_Y3_LATE;
           if (!Y3_LATE) {
             nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
-            momentum_normals<NOISE>(nk, y3);
+            momentum_normals<NOISE, TAB>(nk, y3, Trig);
           }
-          if (F_NORMALS_EARLY) mode_normals<NOISE, 0>(nk, ybf);
-          if (G_NORMALS_EARLY) mode_normals<NOISE, 1>(nk, ybg);
+          if (F_NORMALS_EARLY) mode_normals<NOISE, 0, TAB>(nk, ybf, Trig);
+          if (G_NORMALS_EARLY) mode_normals<NOISE, 1, TAB>(nk, ybg, Trig);
           // only the conserved moments (density, momentum) of the incoming state are needed (physics.cuh, collide_species):
           // the rest of the forward transform is dead code
           moments(go, mg);
@@ -429,7 +438,7 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
           moments(fo, mf);
           if (Y3_LATE) {
             nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
-            momentum_normals<NOISE>(nk, y3);
+            momentum_normals<NOISE, TAB>(nk, y3, Trig);
           }
           if (!RATE1) {  // ... and so do the first PARK_F incoming populations of f (register pressure at the inverse transform)
 #pragma unroll
@@ -437,7 +446,7 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
           }
         }
         collide_prepare<NOISE, FMA_NOISE>(P, grho, gphi, y3, mf, mg, C);
-        if (!F_NORMALS_EARLY) mode_normals<NOISE, 0>(nk, ybf);
+        if (!F_NORMALS_EARLY) mode_normals<NOISE, 0, TAB>(nk, ybf, Trig);
         collide_species<NOISE, 0, RATE1, !RATE1 && BFLBM_F_MOMENT_SPACE, FMA_NOISE>(P, ybf, C, mf);
       } else {
 #pragma unroll
@@ -463,7 +472,7 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
 #pragma unroll
           for (int a = 4; a < Q; ++a) mg[a] = So[(a - 4) * NT + tid];
         }
-        if (!G_NORMALS_EARLY) mode_normals<NOISE, 1>(nk, ybg);
+        if (!G_NORMALS_EARLY) mode_normals<NOISE, 1, TAB>(nk, ybg, Trig);
         collide_species<NOISE, 1, RATE1, !RATE1 && BFLBM_G_MOMENT_SPACE, FMA_NOISE>(P, ybg, C, mg);
       } else {
 #pragma unroll

@@ -128,11 +128,9 @@ int main(int argc, char** argv) {
     const std::vector<int> pairA = {0, 1, 0, 2, 3, 4, 6, 7, 8, 2, 9, 15, 16, 17, 15, 18, 19, 20, 21, 20, 20, 21};
     const std::vector<int> pairB = {0, 1, 1, 2, 3, 4, 6, 7, 8, 6, 9, 15, 16, 17, 16, 18, 19, 20, 21, 21, 18, 18};
     bflbm_sf* structFact = nullptr;
-    if (plot_SF > 0 && R.out_SF_step > 0) {
-      if (!L.handle()) throw std::runtime_error("structure factors need ngpus = 1 (the accumulator works on a whole-box lattice)");
-      if (bflbm_sf_create(L.handle(), (int)pairA.size(), pairA.data(), pairB.data(), nullptr, &structFact))
-        throw std::runtime_error("structure-factor accumulator: creation failed");
-    }
+    if (plot_SF > 0 && R.out_SF_step > 0 &&
+        bflbm_sf_create_multi(L.multi(), (int)pairA.size(), pairA.data(), pairB.data(), nullptr, &structFact))
+      throw std::runtime_error("structure-factor accumulator: creation failed");
 
     // ---- time loop, main_run_job.cpp:329-387 ------------------------------------------------------------------
     std::vector<double> radius_frames;  // main_run_job.cpp:112, 368

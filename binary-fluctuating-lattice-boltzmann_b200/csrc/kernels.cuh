@@ -454,4 +454,49 @@ __global__ void k_count_nonfinite(const double* __restrict__ a, long long n, uns
 
 __global__ void k_philox_test(uint4 ctr, uint2 key, uint4* out) { *out = philox4x32(ctr, key); }
 
+// Deep statistics of the in-kernel Gaussian generator (test hook): the 33 normals of `ncells` cells over `nsteps` steps, i.e. exactly
+// what the step kernels would draw, binned on the device.  hist: nbins equal bins over [lo, hi) + underflow + overflow, all 33
+// streams pooled; joint: JB x JB bins over [-4, 4)^2 of the two normals that come out of ONE Philox word (cos / sin branch of a
+// Box-Muller pair; draws (0,1), (2,3) ... of species f), the place where a dependence would show; mom: sums of n, n^2, n^3, n^4.
+constexpr int NORMAL_JOINT_BINS = 32;
+__global__ void __launch_bounds__(256) k_normal_stats(PhiloxKeys K, long long ncells, long long step0, int nsteps, int nbins, double lo, double hi,
+                                                       unsigned long long* __restrict__ hist, unsigned long long* __restrict__ joint,
+                                                       double* __restrict__ mom) {
+  extern __shared__ unsigned int sh[];  // [nbins + 2] + [JB * JB]
+  unsigned int* sj = sh + nbins + 2;
+  const int nsh = nbins + 2 + NORMAL_JOINT_BINS * NORMAL_JOINT_BINS;
+  for (int i = threadIdx.x; i < nsh; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  const double inv_w = nbins / (hi - lo);
+  double m1 = 0., m2 = 0., m3 = 0., m4 = 0.;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += (long long)gridDim.x * blockDim.x) {
+    for (int s = 0; s < nsteps; ++s) {
+      const NoiseKey nk = make_noise_key(K, (unsigned long long)c, step0 + s);
+      float F[19], G[16];
+      species_normals<0, 0, 18>(nk, F);
+      species_normals<1, 0, 15>(nk, G);
+#pragma unroll
+      for (int j = 0; j < 33; ++j) {
+        const double n = normal_of(j < 18 ? F[j] : G[j - 18]);
+        const double b = floor((n - lo) * inv_w);
+        const int bin = b < 0. ? nbins : (b >= nbins ? nbins + 1 : (int)b);
+        atomicAdd(&sh[bin], 1u);
+        const double n2 = n * n;
+        m1 += n; m2 += n2; m3 += n2 * n; m4 += n2 * n2;
+      }
+#pragma unroll
+      for (int j = 0; j < 18; j += 2) {
+        const double a = normal_of(F[j]), b = normal_of(F[j + 1]);
+        const int ia = (int)floor((a + 4.) * (NORMAL_JOINT_BINS / 8.)), ib = (int)floor((b + 4.) * (NORMAL_JOINT_BINS / 8.));
+        if (ia >= 0 && ia < NORMAL_JOINT_BINS && ib >= 0 && ib < NORMAL_JOINT_BINS) atomicAdd(&sj[ia * NORMAL_JOINT_BINS + ib], 1u);
+      }
+    }
+    // flush often enough that the 32-bit shared counters cannot overflow (<= 33 * nsteps per cell and thread)
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nbins + 2; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+  for (int i = threadIdx.x; i < NORMAL_JOINT_BINS * NORMAL_JOINT_BINS; i += blockDim.x) if (sj[i]) atomicAdd(&joint[i], (unsigned long long)sj[i]);
+  atomicAdd(&mom[0], m1); atomicAdd(&mom[1], m2); atomicAdd(&mom[2], m3); atomicAdd(&mom[3], m4);
+}
+
 }  // namespace bflbm

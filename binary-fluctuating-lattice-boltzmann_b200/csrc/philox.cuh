@@ -7,10 +7,9 @@
 // through Philox4x32-10 (Salmon et al., SC'11) and a Box-Muller transform evaluated in fp32 with the
 // hardware fast paths (MUFU lg2/sin/cos); the amplitude multiply is done in fp64 by the caller.
 // Results therefore do not depend on the decomposition (number of GPUs, tiling) or launch order.
-// One 32-bit Philox word makes one Box-Muller PAIR: 22 bits for the radius uniform (|n| <= 5.65, 4 M levels),
-// 10 bits for the angle (1024 equispaced rays: the marginal of r cos(theta) over M equispaced angles differs from
-// the continuous one only in Bessel terms J_M, J_2M, ... -- nothing below polynomial degree 1024).  That halves
-// the Philox work of the first version (32 + 32 bits per pair): 5 blocks per cell instead of 9.
+// One 32-bit Philox word makes one Box-Muller PAIR: 22 bits for the radius uniform (|n| <= 5.65, 4 M levels) and a 16-bit angle
+// built from all 32 bits (angle_index below; the marginal of r cos(theta) over M equispaced angles differs from the continuous
+// one only in Bessel terms J_M, J_2M, ...).  5 Philox blocks per cell (the first version spent 32 + 32 bits per pair: 9 blocks).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -89,16 +88,53 @@ __device__ __forceinline__ float normal_f32(float y) { return fmaf(y, 16.f, -24.
 // the standard normal itself (observers, tests): exact, y has 24 significant bits
 __device__ __forceinline__ double normal_of(float y) { return NRM_SCALE * (widen_pos(y) - NRM_BIAS); }
 
+// Angle of a word.  10 bits (bits 0..9, disjoint from the radius bits 10..31) put the pair (n0, n1) on one of 1024 rays: invisible
+// in every marginal and in the pooled statistics of 1e10 normals, but a 2-D histogram of 2.8e9 pairs sees it (chi2/dof = 1.9 on
+// 32 x 32 bins, tests/test_gpu_noise_quality.py).  16 bits: j = (64 w + (w >> 10)) mod 2^16 -- the coarse angle is bits 0..9
+// plus radius bits (a one-time pad: uniform and independent of the radius), the fine angle is the radius's six lowest bits,
+// which move the radius by < 2^-16 relative.  65 536 rays, every one of the 1024 coarse directions present at every radius level
+// (the tails stay isotropic; taking the radius's low bits as the angle's HIGH bits does not: chi2 = 23 764 / 219 at 1e10,
+// profiles/README.md).  One more integer instruction per pair than the 10-bit form.
+#ifndef BFLBM_ANGLE_BITS
+#define BFLBM_ANGLE_BITS 16
+#endif
+#ifndef BFLBM_TRIG_TABLE  // 1: the fused kernels read (cos, sin) from a 1024-entry shared-memory table (10-bit angle only)
+#define BFLBM_TRIG_TABLE 0
+#endif
+#define BFLBM_TRIG_TABLE_ALLOWED BFLBM_TRIG_TABLE
+constexpr uint32_t ANGLE_MASK = (1u << BFLBM_ANGLE_BITS) - 1u;
+__device__ __forceinline__ uint32_t angle_index(uint32_t w) {
+  return (BFLBM_ANGLE_BITS == 10 ? w : (w << 6) + (w >> 10)) & ANGLE_MASK;
+}
+constexpr float ANGLE_STEP = 6.283185307179586f / (float)(1u << BFLBM_ANGLE_BITS);  // 2 pi / 2^bits
 // one Philox word -> two independent standard normals, biased form
 __device__ __forceinline__ void box_muller(uint32_t w, float& y0, float& y1) {
-  // U in (0,1): (w>>10 + 0.5) / 2^22 ; theta = 2 pi (w & 1023 + 0.5) / 1024 ; both conversions are exact in fp32
+  // U in (0,1): (w>>10 + 0.5) / 2^22 ; theta = 2 pi (angle bits + 0.5) / 2^bits ; both conversions are exact in fp32
   const float U = fmaf((float)(w >> 10), 2.384185791015625e-07f, 1.1920928955078125e-07f);
   // r / 16 = sqrt(-2 ln U) / 16 = sqrt(-(2 ln2 / 256) lg2 U).  lg2.approx of a U just below 1 may come out as +2^-22
   // instead of -0: the |.| (a free operand modifier of MUFU.SQRT) keeps the argument non-negative.
   const float r = fast_sqrt(fabsf(5.4152123481245727e-03f * fast_lg2(U)));
-  const float th = fmaf((float)(w & 1023u), 6.1359231515425647e-03f, 3.0679615757712823e-03f);
+  const float th = fmaf((float)angle_index(w), ANGLE_STEP, 0.5f * ANGLE_STEP);
   y0 = fmaf(r, fast_cos(th), NRM_BIAS_F);
   y1 = fmaf(r, fast_sin(th), NRM_BIAS_F);
+}
+
+// The same pair with (cos, sin) of the word's angle read from a 1024-entry table in shared memory that was filled with exactly the
+// two MUFU results above (fill_trig_table): a memoisation, bit-identical normals, 2 instructions (mask, LDS.64) instead of 7
+// (mask, int->float, fma, 2 x (range-reduction multiply + MUFU)) per pair.
+__device__ __forceinline__ void fill_trig_table(float2* tab, int tid, int nthreads) {
+  static_assert(BFLBM_ANGLE_BITS == 10 || !BFLBM_TRIG_TABLE_ALLOWED, "the shared-memory trig table needs the 10-bit angle");
+  for (int j = tid; j < 1024; j += nthreads) {
+    const float th = fmaf((float)j, ANGLE_STEP, 0.5f * ANGLE_STEP);
+    tab[j] = make_float2(fast_cos(th), fast_sin(th));
+  }
+}
+__device__ __forceinline__ void box_muller(uint32_t w, const float2* __restrict__ tab, float& y0, float& y1) {
+  const float U = fmaf((float)(w >> 10), 2.384185791015625e-07f, 1.1920928955078125e-07f);
+  const float r = fast_sqrt(fabsf(5.4152123481245727e-03f * fast_lg2(U)));
+  const float2 cs = tab[w & 1023u];
+  y0 = fmaf(r, cs.x, NRM_BIAS_F);
+  y1 = fmaf(r, cs.y, NRM_BIAS_F);
 }
 
 // Philox counter layout: {cell_lo, cell_hi, step_lo, (step_hi & 0xffffff) | block << 24}, key = seed.
@@ -133,15 +169,17 @@ __device__ __forceinline__ uint4 noise_block_words(const NoiseKey& k, int block)
 __device__ __forceinline__ uint32_t word_of(const uint4& r, int w) { return w == 0 ? r.x : (w == 1 ? r.y : (w == 2 ? r.z : r.w)); }
 
 // normals lo .. hi-1 of species s into n[0 .. hi-lo-1] (lo even); compile-time bounds, everything unrolls
-template <int S, int LO, int HI>
-__device__ __forceinline__ void species_normals(const NoiseKey& k, float (&n)[HI - LO + 1]) {
+// TAB: trig is the shared-memory (cos, sin) table (compile-time switch: a pointer test would keep both code paths alive)
+template <int S, int LO, int HI, bool TAB = false>
+__device__ __forceinline__ void species_normals(const NoiseKey& k, float (&n)[HI - LO + 1], const float2* __restrict__ trig = nullptr) {
   static_assert((LO & 1) == 0, "pairs start at even indices");
   uint4 r = make_uint4(0, 0, 0, 0);
 #pragma unroll
   for (int j = LO; j < HI; j += 2) {
     if (j == LO || (j & 7) == 0) r = noise_block_words(k, noise_block(S, j));
     float a, b;
-    box_muller(word_of(r, noise_word(j)), a, b);
+    if (TAB) box_muller(word_of(r, noise_word(j)), trig, a, b);
+    else     box_muller(word_of(r, noise_word(j)), a, b);
     n[j - LO] = a;
     n[j - LO + 1] = b;  // the array has one spare slot for an odd count
   }

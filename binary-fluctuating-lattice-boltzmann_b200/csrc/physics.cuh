@@ -193,19 +193,19 @@ __device__ __forceinline__ void collide_species(const DevParams& P, const float 
 // (1 - w) of the species: the weight of the old populations in the post-collision state
 __device__ __forceinline__ double keep_of(const DevParams& P, int species) { return 1. - (species == 0 ? P.rate_f : P.rate_g); }
 
-template <bool NOISE>
-__device__ __forceinline__ void momentum_normals(const NoiseKey& nk, float (&y3)[3]) {
+template <bool NOISE, bool TAB = false>
+__device__ __forceinline__ void momentum_normals(const NoiseKey& nk, float (&y3)[3], const float2* __restrict__ trig = nullptr) {
   float y0[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  if (NOISE) species_normals<0, 0, 4>(nk, y0);
+  if (NOISE) species_normals<0, 0, 4, TAB>(nk, y0, trig);
   y3[0] = y0[0]; y3[1] = y0[1]; y3[2] = y0[2];
 }
-template <bool NOISE, int SPECIES>
-__device__ __forceinline__ void mode_normals(const NoiseKey& nk, float (&yb)[15]) {
+template <bool NOISE, int SPECIES, bool TAB = false>
+__device__ __forceinline__ void mode_normals(const NoiseKey& nk, float (&yb)[15], const float2* __restrict__ trig = nullptr) {
   if (NOISE) {
     // modes 4..18 : normals F[3..17] (the pair F[2], F[3] comes from block 0, shared with the momentum draws) / G[0..14]
     constexpr int LO = SPECIES == 0 ? 2 : 0, HI = SPECIES == 0 ? 18 : 15;
     float t[HI - LO + 1];
-    species_normals<SPECIES, LO, HI>(nk, t);
+    species_normals<SPECIES, LO, HI, TAB>(nk, t, trig);
 #pragma unroll
     for (int a = 4; a < Q; ++a) yb[a - 4] = t[mode_index(SPECIES, a) - LO];
   } else {

@@ -59,7 +59,8 @@ __global__ void k_sf_expand(int nx, int ny, int nz, int nxh, const double* __res
 }  // namespace
 
 struct bflbm_sf {
-  bflbm_lattice* lat = nullptr;
+  std::vector<bflbm_lattice*> lats;  // the whole-box lattice, or every slab of a box (bflbm_sf_create_multi)
+  int device = 0;                    // where the assembled fields, the FFTs and the running sums live (the first lattice's GPU)
   int nx = 0, ny = 0, nz = 0, nxh = 0, npairs = 0, nvars = 0;
   long long n = 0, nhalf = 0, samples = 0;
   std::vector<int> vars;  // distinct hydrovs components, in order of first use
@@ -73,14 +74,25 @@ struct bflbm_sf {
 
 extern "C" {
 
-int bflbm_sf_create(bflbm_lattice* h, int npairs, const int* pairA, const int* pairB, const double* var_scaling, bflbm_sf** out) {
-  if (!h || !out || npairs < 1 || !pairA || !pairB) return sf_fail(BFLBM_ERR_ARG, "bad argument");
+static int sf_create_common(const std::vector<bflbm_lattice*>& lats, int npairs, const int* pairA, const int* pairB, const double* var_scaling,
+                            bflbm_sf** out) {
+  if (lats.empty() || !lats[0] || !out || npairs < 1 || !pairA || !pairB) return sf_fail(BFLBM_ERR_ARG, "bad argument");
   *out = nullptr;
   int nx, ny, nz, z0, nzg;
-  if (bflbm_get_dims(h, &nx, &ny, &nz, &z0, &nzg)) return sf_fail(BFLBM_ERR_ARG, "cannot query the lattice");
-  if (nz != nzg) return sf_fail(BFLBM_ERR_ARG, "structure factors need a whole-box lattice (one GPU holds the box)");
+  if (bflbm_get_dims(lats[0], &nx, &ny, &nz, &z0, &nzg)) return sf_fail(BFLBM_ERR_ARG, "cannot query the lattice");
+  long long covered = 0;
+  for (bflbm_lattice* l : lats) {
+    int lx, ly, lz, l0, lg;
+    if (!l || bflbm_get_dims(l, &lx, &ly, &lz, &l0, &lg) || lx != nx || ly != ny || lg != nzg) return sf_fail(BFLBM_ERR_ARG, "lattices of different boxes");
+    covered += lz;
+  }
+  if (covered != nzg) return sf_fail(BFLBM_ERR_ARG, "structure factors need the whole box: one whole-box lattice, or all slabs (bflbm_sf_create_multi)");
+  nz = nzg;
   bflbm_sf* s = new bflbm_sf;
-  s->lat = h; s->nx = nx; s->ny = ny; s->nz = nz; s->nxh = nx / 2 + 1; s->npairs = npairs;
+  s->lats = lats;
+  s->device = bflbm_get_device(lats[0]);
+  SF_CU(cudaSetDevice(s->device));
+  s->nx = nx; s->ny = ny; s->nz = nz; s->nxh = nx / 2 + 1; s->npairs = npairs;
   s->n = (long long)nx * ny * nz;
   s->nhalf = (long long)s->nxh * ny * nz;
   std::vector<int> sa(npairs), sb(npairs);
@@ -121,8 +133,18 @@ int bflbm_sf_create(bflbm_lattice* h, int npairs, const int* pairA, const int* p
   return 0;
 }
 
+int bflbm_sf_create(bflbm_lattice* h, int npairs, const int* pairA, const int* pairB, const double* var_scaling, bflbm_sf** out) {
+  return sf_create_common(std::vector<bflbm_lattice*>{h}, npairs, pairA, pairB, var_scaling, out);
+}
+int bflbm_sf_create_multi(bflbm_multi* m, int npairs, const int* pairA, const int* pairB, const double* var_scaling, bflbm_sf** out) {
+  std::vector<bflbm_lattice*> lats;
+  for (int i = 0; i < bflbm_multi_count(m); ++i) lats.push_back(bflbm_multi_slab(m, i));
+  return sf_create_common(lats, npairs, pairA, pairB, var_scaling, out);
+}
+
 int bflbm_sf_destroy(bflbm_sf* s) {
   if (!s) return 0;
+  cudaSetDevice(s->device);
   if (s->have_plan) cufftDestroy(s->plan);
   cudaFree(s->hydro); cudaFree(s->spec); cudaFree(s->acc_re); cudaFree(s->acc_im); cudaFree(s->full);
   cudaFree(s->scale); cudaFree(s->slotA); cudaFree(s->slotB);
@@ -132,6 +154,7 @@ int bflbm_sf_destroy(bflbm_sf* s) {
 
 int bflbm_sf_reset(bflbm_sf* s) {
   if (!s) return sf_fail(BFLBM_ERR_ARG, "null handle");
+  SF_CU(cudaSetDevice(s->device));
   SF_CU(cudaMemset(s->acc_re, 0, (size_t)s->npairs * s->nhalf * sizeof(double)));
   SF_CU(cudaMemset(s->acc_im, 0, (size_t)s->npairs * s->nhalf * sizeof(double)));
   s->samples = 0;
@@ -142,8 +165,13 @@ long long bflbm_sf_samples(const bflbm_sf* s) { return s ? s->samples : -1; }
 
 int bflbm_sf_accumulate(bflbm_sf* s) {
   if (!s) return sf_fail(BFLBM_ERR_ARG, "null handle");
-  int rc = bflbm_get_hydrovars_device(s->lat, s->hydro);  // synchronises the lattice's stream
-  if (rc) return sf_fail(rc, bflbm_last_error());
+  // every lattice writes its planes of the 22 fields into the assembled array (a peer copy from the other GPUs' slabs);
+  // each call synchronises that lattice's stream
+  for (bflbm_lattice* l : s->lats) {
+    const int rc = bflbm_get_hydrovars_device_into_global(l, s->hydro);
+    if (rc) return sf_fail(rc, bflbm_last_error());
+  }
+  SF_CU(cudaSetDevice(s->device));
   for (int v = 0; v < s->nvars; ++v)
     if (cufftExecD2Z(s->plan, s->hydro + (long long)s->vars[v] * s->n, s->spec + (long long)v * s->nhalf) != CUFFT_SUCCESS)
       return sf_fail(BFLBM_ERR_CUDA, "cufftExecD2Z failed");
@@ -159,6 +187,7 @@ int bflbm_sf_accumulate(bflbm_sf* s) {
 int bflbm_sf_get(bflbm_sf* s, int zero_avg, double* real, double* imag) {
   if (!s || !real) return sf_fail(BFLBM_ERR_ARG, "null argument");
   if (s->samples == 0) return sf_fail(BFLBM_ERR_STATE, "no samples accumulated");
+  SF_CU(cudaSetDevice(s->device));
   const dim3 block(128), grid((s->nx + 127) / 128, s->ny, s->nz);
   for (int p = 0; p < s->npairs; ++p) {
     k_sf_expand<<<grid, block>>>(s->nx, s->ny, s->nz, s->nxh, s->acc_re + (long long)p * s->nhalf, s->acc_im + (long long)p * s->nhalf,

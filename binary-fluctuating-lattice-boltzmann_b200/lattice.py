@@ -94,6 +94,8 @@ def load_library() -> ctypes.CDLL:
         "bflbm_get_normals": (ip, [vp, vp]),
         "bflbm_get_hydrovars_device": (ip, [vp, vp]),
         "bflbm_get_hydrovars_bar_device": (ip, [vp, vp]),
+        "bflbm_get_hydrovars_device_into_global": (ip, [vp, vp]),
+        "bflbm_get_device": (ip, [vp]),
         "bflbm_get_populations_device": (ip, [vp, vp, vp]),
         "bflbm_center_of_mass": (ip, [vp, vp, vp]),
         "bflbm_total_mass": (ip, [vp, vp, vp]),
@@ -113,6 +115,7 @@ def load_library() -> ctypes.CDLL:
         "bflbm_second_moments": (ip, [vp, vp]),
         "bflbm_droplet_covariance": (ip, [vp, vp, vp, vp]),
         "bflbm_debug_philox": (ip, [vp, vp, vp]),
+        "bflbm_debug_normal_statistics": (ip, [ctypes.c_ulonglong, ctypes.c_longlong, ctypes.c_longlong, ip, ip, dp, dp, vp, vp, vp]),
         "bflbm_covariance_from_moments": (ip, [vp, vp, vp, vp]),
         "bflbm_set_reference_state": (ip, [vp, vp, vp, vp]),
         "bflbm_fit_droplet": (ip, [vp, ip, dp, ip, dp, dp, dp, dp, dp, vp, ctypes.POINTER(ip)]),

@@ -26,6 +26,7 @@ def _load():
         lib = ctypes.CDLL(_build.SF_LIB)
         vp, ip, dpp = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p
         lib.bflbm_sf_create.restype, lib.bflbm_sf_create.argtypes = ip, [vp, ip, dpp, dpp, dpp, ctypes.POINTER(vp)]
+        lib.bflbm_sf_create_multi.restype, lib.bflbm_sf_create_multi.argtypes = ip, [vp, ip, dpp, dpp, dpp, ctypes.POINTER(vp)]
         lib.bflbm_sf_destroy.restype, lib.bflbm_sf_destroy.argtypes = ip, [vp]
         lib.bflbm_sf_accumulate.restype, lib.bflbm_sf_accumulate.argtypes = ip, [vp]
         lib.bflbm_sf_reset.restype, lib.bflbm_sf_reset.argtypes = ip, [vp]
@@ -36,7 +37,7 @@ def _load():
 
 
 class StructureFactor:
-    """StructFact(ba, dm, var_names, var_scaling, pairA, pairB) for a whole-box Lattice."""
+    """StructFact(ba, dm, var_names, var_scaling, pairA, pairB) for a whole-box Lattice or a MultiLattice (slabs on several GPUs)."""
 
     def __init__(self, lat: Lattice, pairs=REFERENCE_PAIRS, var_scaling=None):
         self.lib = _load()
@@ -46,8 +47,8 @@ class StructureFactor:
         b = np.ascontiguousarray([p[1] for p in self.pairs], dtype=np.int32)
         sc = None if var_scaling is None else np.ascontiguousarray(var_scaling, dtype=np.float64)
         self.h = ctypes.c_void_p()
-        rc = self.lib.bflbm_sf_create(lat.h, len(self.pairs), a.ctypes.data, b.ctypes.data, None if sc is None else sc.ctypes.data,
-                                      ctypes.byref(self.h))
+        create = self.lib.bflbm_sf_create_multi if hasattr(lat, "ngpus") else self.lib.bflbm_sf_create
+        rc = create(lat.h, len(self.pairs), a.ctypes.data, b.ctypes.data, None if sc is None else sc.ctypes.data, ctypes.byref(self.h))
         if rc:
             raise BflbmError(f"bflbm_sf_create failed ({rc})")
 

@@ -132,6 +132,10 @@ int bflbm_get_normals(bflbm_lattice* h, double* out33);
 /* Same getters into DEVICE memory owned by the caller (full local size, same layout). */
 int bflbm_get_hydrovars_device(bflbm_lattice* h, double* dev_out22);
 int bflbm_get_hydrovars_bar_device(bflbm_lattice* h, double* dev_out9);
+/* Same into a DEVICE array of the whole box, (22, nz_global, ny, nx), which may live on another GPU of this process (a peer
+ * copy): how the structure-factor accumulator assembles a slab-decomposed field on one device. */
+int bflbm_get_hydrovars_device_into_global(bflbm_lattice* h, double* dev_global22);
+int bflbm_get_device(const bflbm_lattice* h); /* CUDA device of the lattice */
 int bflbm_get_populations_device(bflbm_lattice* h, double* dev_f, double* dev_g);
 
 /* Host arrays of the WHOLE box, shape (ncomp, nz_global, ny, nx) -- the MultiFab a reference driver holds.  A slab reads /
@@ -262,6 +266,12 @@ size_t bflbm_device_bytes(const bflbm_lattice* h);
 
 /* Philox4x32-10 block function (test hook for known-answer vectors; runs on the device). */
 int bflbm_debug_philox(const unsigned int ctr[4], const unsigned int key[2], unsigned int out[4]);
+
+/* Deep statistics of the in-kernel Gaussian generator (test hook): the 33 normals of ncells cells over nsteps steps binned on the
+ * device.  hist[nbins + 2]: equal bins over [lo, hi), then underflow, overflow; joint[32 * 32]: the two normals of one Box-Muller
+ * pair over [-4, 4)^2; moments4: sums of n, n^2, n^3, n^4.  10^10 normals take about a second. */
+int bflbm_debug_normal_statistics(unsigned long long seed, long long ncells, long long step0, int nsteps, int nbins, double lo, double hi,
+                                  unsigned long long* hist, unsigned long long* joint, double* moments4);
 
 const char* bflbm_last_error(void);
 const char* bflbm_version(void);

@@ -10,7 +10,9 @@
  * The 22 hydrodynamic fields never leave the GPU: observer kernel -> cuFFT D2Z -> running sums of A_k conj(B_k).
  *
  * A separate shared library (libbflbm_sf.so, links cuFFT) on top of the public C ABI of libbflbm.so, so that the
- * step library itself carries no FFT dependency.  Whole-box lattices only (one GPU holds the box).
+ * step library itself carries no FFT dependency.  The box may be one whole-box lattice or the slabs of a bflbm_multi (one
+ * process, several GPUs: main_run_job.cpp:342-349 runs FortStructure on the distributed MultiFab): every slab then copies its
+ * planes of the 22 fields peer-to-peer into one assembled array on the first slab's GPU, where the transforms and sums live.
  */
 #ifndef BFLBM_SF_H_
 #define BFLBM_SF_H_
@@ -26,6 +28,8 @@ typedef struct bflbm_sf bflbm_sf; /* opaque */
 /* pairA/pairB: npairs component indices into hydrovs (0..21, VariableNames order), like StructFact's pair lists.
  * var_scaling: npairs factors applied to the accumulated pair (NULL = all 1, as at main_run_job.cpp:306-308). */
 int bflbm_sf_create(bflbm_lattice* h, int npairs, const int* pairA, const int* pairB, const double* var_scaling, bflbm_sf** out);
+/* the same for a box decomposed over the GPUs of this process */
+int bflbm_sf_create_multi(bflbm_multi* m, int npairs, const int* pairA, const int* pairB, const double* var_scaling, bflbm_sf** out);
 int bflbm_sf_destroy(bflbm_sf* s);
 /* StructFact::FortStructure(hydrovs, reset = 0): transform the current hydrovs and add A_k conj(B_k) of every pair */
 int bflbm_sf_accumulate(bflbm_sf* s);

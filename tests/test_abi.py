@@ -31,7 +31,7 @@ def test_structure_factor_library_exports_its_header(bflbm):
     src = open(os.path.join(ROOT, "include", "bflbm_sf.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = sorted(set(re.findall(r"\b(bflbm_sf_[a-z0-9_]+)\s*\(", src)))
-    assert len(names) == 6
+    assert len(names) == 7
     assert not [n for n in names if not hasattr(lib, n)]
 
 

@@ -70,6 +70,30 @@ def test_multi_lattice_bitwise_equal_to_whole_box(bflbm, ngpus):
         assert np.allclose(W.droplet_covariance()[2], M.droplet_covariance()[2], rtol=1e-10)
 
 
+@pytest.mark.parametrize("ngpus", [2, 4])
+def test_structure_factor_on_slabs_equals_whole_box(bflbm, ngpus):
+    """BASELINE configs[3] analyses S(k) on the decomposition: the accumulator assembles the slabs' hydro fields on one GPU by peer
+    copies and transforms there (main_run_job.cpp:342-349 runs FortStructure on the distributed MultiFab).  Same fields => same
+    spectra as the one-GPU accumulator, bit for bit."""
+    if _ngpus() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    nx, ny, nz, lz = 16, 24, 8 * ngpus, 4
+    prm = bflbm.Params(kBT=1e-5, alpha0=0.0, seed=12)
+    pairs = [(0, 0), (1, 1), (0, 1), (15, 16), (2, 6)]
+    with bflbm.Lattice(nx, ny, nz, params=prm) as W, bflbm.MultiLattice(nx, ny, nz, params=prm, ngpus=ngpus, brick_lz=lz) as M:
+        W.set_tiling(lz)
+        W.init_mixture()
+        M.init_mixture()
+        with bflbm.StructureFactor(W, pairs) as SW, bflbm.StructureFactor(M, pairs) as SM:
+            for _ in range(4):
+                W.step(5)
+                M.step(5)
+                SW.fort_structure()
+                SM.fort_structure()
+            a, b = SW.result(imag=True), SM.result(imag=True)
+            assert SM.samples == 4 and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
 def _read_plotfile(path):
     hdr = open(os.path.join(path, "Header")).read().split("\n")
     ncomp = int(hdr[1])

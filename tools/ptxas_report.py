@@ -15,7 +15,7 @@ if "-o" in args:
     out = args[i + 1]
     del args[i:i + 2]
 cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
-       "-Xptxas", "-v"] + args + [os.path.join(PKG, "csrc", "capi.cu"), "-o", out]
+       "-Xptxas", "-v"] + args + [os.path.join(PKG, "csrc", "capi.cu"), os.path.join(PKG, "csrc", "multi.cu"), "-o", out]
 r = subprocess.run(cmd, capture_output=True, text=True)
 if r.returncode:
     sys.stderr.write(r.stderr)
