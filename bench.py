@@ -444,14 +444,19 @@ def run_e2e(a, b, np, torch, lat, stepper, world, cells, cells_local):
     _check(lib.bflbm_get_populations(lat.h, fn.ctypes.data, gn.ctypes.data))  # untimed: makes the host checkpoint
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    _check(lib.bflbm_init_from_populations(lat.h, fn.ctypes.data, gn.ctypes.data))
+    _check(lib.bflbm_init_from_populations(lat.h, fn.ctypes.data, gn.ctypes.data))  # returns when the host buffers are free again
+    t1 = time.perf_counter()
     _check(lib.bflbm_step(lat.h, nsteps))
+    _check(lib.bflbm_sync(lat.h))
+    t2 = time.perf_counter()
     _check(lib.bflbm_get_hydrovars_bar(lat.h, out.numpy().ctypes.data))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     mass = float(out[0].sum())
     return {"value": cells * nsteps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * 19 * 8 * cells_local / nsteps,
             "d2h_bytes_per_step": 9 * 8 * cells_local / nsteps, "steps_per_interval": nsteps, "seconds": dt, "pinned_host": pinned,
+            "phases_s": {"upload": t1 - t0, "steps": t2 - t1, "download": t0 + dt - t2},
+            "h2d_gb_per_s": 2 * 19 * 8 * cells_local / (t1 - t0) / 1e9,
             "what": "bflbm_init_from_populations(host f,g) + bflbm_step(200) + bflbm_get_hydrovars_bar(host), wall clock",
             "result_mass_rho": mass}
 

@@ -1105,6 +1105,7 @@ int bflbm_halo_refresh_end(bflbm_lattice* h) {
   if (rc) return rc;
   double* const self[2] = {h->send[1], h->send[0]};
   if ((rc = unpack_halo(h, h->whole_box ? self : h->recv))) return rc;
+  h->ghosts_stale = false;
   h->ref_relative = true;  // restart entry: LBM_init passes com - com_ref (LBM_binary.H:651-653)
   return update_ref_shift(h);
 }

@@ -262,15 +262,21 @@ class SlabLattice:
         dist.barrier()
         t0 = time.perf_counter()
         self.init_from_populations_slab(fg[0], fg[1])
+        t1 = time.perf_counter()
         self.step(nsteps)
+        _check(lat.lib.bflbm_sync(lat.h))
+        t2 = time.perf_counter()
         _check(lat.lib.bflbm_get_hydrovars_bar(lat.h, out_pinned.numpy().ctypes.data))
         torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device=self.device, dtype=torch.float64)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        dt = float(dt.item())
+        t3 = time.perf_counter()
+        ph = torch.tensor([t3 - t0, t1 - t0, t2 - t1, t3 - t2], device=self.device, dtype=torch.float64)
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)  # slowest rank per phase; the interval is the slowest rank's total
+        dt, up, st, down = (float(v) for v in ph.tolist())
         cells_local = self.nzl * lat.ny * lat.nx
         cells = lat.nx * lat.ny * self.nz_global
         return {"value": cells * nsteps / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 2 * 19 * 8 * (cells_local + 2 * lat.ny * lat.nx) / nsteps,
                 "d2h_bytes_per_step": 9 * 8 * cells_local / nsteps, "steps_per_interval": nsteps, "seconds": dt, "pinned_host": pinned,
+                "phases_s": {"upload": up, "steps": st, "download": down},
+                "h2d_gb_per_s_per_gpu": 2 * 19 * 8 * (cells_local + 2 * lat.ny * lat.nx) / up / 1e9,
                 "what": "per rank: bflbm_init_from_populations_slab(host f,g) + halo refresh + nsteps x (step_begin, NCCL ring exchange, "
                         "step_end) + bflbm_get_hydrovars_bar(host); wall clock, max over ranks"}

@@ -51,6 +51,11 @@ def _worker(rank, world, port, nz, q):
             exchange_ring(send_lo, send_hi, recv_lo, recv_hi, rank, world)
             assert np.array_equal(recv_lo.numpy(), glob[(z0 - 1) % nz]), "ghost plane below = neighbour's top plane"
             assert np.array_equal(recv_hi.numpy(), glob[(z0 + nzl) % nz]), "ghost plane above = neighbour's bottom plane"
+        # peer-mode plumbing: every rank publishes its mailbox handle once and picks its two ring neighbours' (64 opaque bytes)
+        from bflbm_b200.distributed import gather_ring_handles, neighbours
+        lo, hi = gather_ring_handles(bytes([rank]) * 64, rank, world)
+        nlo, nhi = neighbours(world, rank)
+        assert lo == bytes([nlo]) * 64 and hi == bytes([nhi]) * 64
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
@@ -74,7 +79,8 @@ def test_ring_exchange_gloo(world, nz):
 
 
 def test_single_rank_exchange_is_self_wrap():
-    from bflbm_b200.distributed import exchange_ring
+    from bflbm_b200.distributed import exchange_ring, gather_ring_handles
+    assert gather_ring_handles(b"x" * 64, 0, 1) == (b"x" * 64, b"x" * 64)
     a, b = torch.arange(4.0), torch.arange(4.0) + 10
     ra, rb = torch.empty(4), torch.empty(4)
     exchange_ring(a, b, ra, rb, 0, 1)
