@@ -580,3 +580,12 @@ def test_degenerate_and_ragged_boxes_vs_oracle(bflbm, oracle_mod, shape, kbt):
             fo, go = O.populations()
             assert rel_err(fl, fo) <= 10 * TOL and rel_err(gl, go) <= 10 * TOL, f"step {s}"
             assert_hydro_close(lat.hydrovars(), O.hydrovars(), 10 * TOL, f"step {s}")
+
+
+# The checker on the GPU box is the C port; its pin to the reference's own headers (oracle/_ref, prebuilt, travels with the
+# snapshot) is re-run there too, so that the `-m gpu` log carries it next to the parity results.
+@pytest.mark.gpu
+def test_checker_is_pinned_to_reference_headers_on_this_box(oracle_mod):
+    import test_oracle
+    test_oracle.test_port_matches_reference_headers_bitwise(oracle_mod)
+    test_oracle.test_port_reference_state_noise_matches_ref_build_bitwise(oracle_mod)
