@@ -70,9 +70,17 @@ inline BrickGrid make_brick_grid(const Geom& G, int lz_request = 0, int nthreads
   B.by = (G.ny + B.ty - 1) / B.ty;
   int lz = lz_request;
   if (lz <= 0) {
-    // enough CTAs to balance 148 SMs x 2 resident CTAs, but bricks as tall as possible (less shell traffic)
-    lz = 32;
-    while (lz > 4 && (long long)B.bx * B.by * ((G.nzl + lz - 1) / lz) < 148 * 2 * 6) lz >>= 1;
+    // Bricks as tall as possible (a brick of height lz costs (lz + ~0.6) planes and (lz + 2) / lz of the shell traffic:
+    // lz = 4 is 12 % slower than 32 at equal fill), under two conditions measured in profiles/r2m_tiling_sweep.txt: the
+    // kernel is bandwidth bound, so one partial wave of >= 0.8 x (148 SMs x 2 CTAs) already saturates HBM (128^3: 256
+    // CTAs of height 32 beat 2048 of height 4 by 6 %), and between one and two waves the tail costs more than the
+    // shorter bricks (160^3: 500 CTAs lose to 1000).
+    const long long slots = 148 * 2;
+    lz = 4;
+    for (int c = 32; c > 4; c >>= 1) {
+      const long long ctas = (long long)B.bx * B.by * ((G.nzl + c - 1) / c);
+      if ((ctas >= (slots * 8) / 10 && ctas <= slots) || ctas >= 2 * slots) { lz = c; break; }
+    }
   }
   if (lz > G.nzl) lz = G.nzl;
   if (lz < 2) lz = 2;
