@@ -13,8 +13,13 @@ import bflbm_b200 as B
 out = open(sys.argv[1], "w") if len(sys.argv) > 1 else sys.stdout
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)  # torch.cuda.Event records on torch's current stream: make it the lattice's
+if len(sys.argv) > 2 and sys.argv[2] == "nt128":  # 128-thread CTAs (experiment knob): small and mid-size boxes only
+    os.environ["BFLBM_CTA_THREADS"] = "128"
 sizes = [(64, 64, 64), (96, 96, 96), (128, 128, 128), (160, 160, 160), (192, 192, 192), (256, 256, 256), (128, 128, 512), (512, 512, 64)]
 kbts = [1e-5, 0.0]
+if len(sys.argv) > 2:
+    sizes = [(32, 32, 32), (64, 64, 64), (96, 96, 96), (128, 128, 128)] if sys.argv[2] == "nt128" else [s for s in sizes if s[0] in (96, 128, 160, 192)]
+    kbts = [1e-5]
 for (nx, ny, nz) in sizes:
     cells = nx * ny * nz
     for kbt in kbts:
