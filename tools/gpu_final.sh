@@ -10,6 +10,8 @@ BFLBM_RATE1=0 python bench.py --no-e2e --no-cpu --steps 20 > $o/${tag}_bench_n1_
 # the reference's own job sizes (Parameters:1-37), library's choice of kernels, CUDA-graph replay
 python bench.py --algo auto --nx 32 --ny 32 --nz 32 --kbt 0 --steps 4096 --warmup 128 --no-e2e --no-cpu > $o/${tag}_bench_32cubed_det.json 2>/dev/null
 python bench.py --algo auto --nx 8 --ny 256 --nz 64 --steps 4096 --warmup 128 --no-e2e --no-cpu > $o/${tag}_bench_8x256x64_noise.json 2>/dev/null
+python bench.py --algo auto --nx 64 --ny 64 --nz 64 --steps 4096 --warmup 128 --no-e2e --no-cpu > $o/${tag}_bench_64cubed_noise.json 2>/dev/null
+python bench.py --algo auto --nx 128 --ny 128 --nz 128 --steps 1024 --warmup 64 --no-e2e --no-cpu > $o/${tag}_bench_128cubed_noise.json 2>/dev/null
 # launch list of the bench command (cold-cache, serialised: compare shares)
 CMD="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu"
 $CMD > $o/${tag}_launch_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches_512cubed.csv $CMD > $o/${tag}_launch_ncu.log 2>&1
