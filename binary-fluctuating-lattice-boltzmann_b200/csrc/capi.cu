@@ -120,6 +120,12 @@ struct bflbm_lattice {
   // optional per-kernel timing: events ev[0..4] bracket {step kernel, fold, pack, unpack}
   bool profiling = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // deferred mode (bflbm_set_profiling(h, 2)): one set of five events per step from a pool, read back only when the pool is
+  // full or the totals are asked for -- no host synchronisation inside a timed region
+  static constexpr int PROF_POOL_STEPS = 128;
+  std::vector<cudaEvent_t> evpool;
+  bool prof_deferred = false;
+  int prof_slot = 0;
   double prof_ms[4] = {0., 0., 0., 0.};
   long long prof_steps = 0;
 };
@@ -178,17 +184,32 @@ cudaError_t set_fused_smem() {
 }
 
 inline void mark(bflbm_lattice* h, int i) {
-  if (h->profiling) cudaEventRecord(h->ev[i], h->stream);
+  if (h->profiling) cudaEventRecord(h->prof_deferred ? h->evpool[(size_t)h->prof_slot * 5 + i] : h->ev[i], h->stream);
 }
-// call after mark(4): folds the four intervals of one step into the totals (synchronises the stream)
-inline void profile_collect(bflbm_lattice* h) {
-  if (!h->profiling) return;
-  cudaEventSynchronize(h->ev[4]);
+inline void profile_add(bflbm_lattice* h, const cudaEvent_t* ev) {
   for (int i = 0; i < 4; ++i) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) h->prof_ms[i] += ms;
+    if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) h->prof_ms[i] += ms;
   }
   ++h->prof_steps;
+}
+// deferred mode: read back the steps recorded so far (synchronises on the last of them)
+inline void profile_flush(bflbm_lattice* h) {
+  if (!h->prof_deferred || h->prof_slot == 0) return;
+  cudaEventSynchronize(h->evpool[(size_t)(h->prof_slot - 1) * 5 + 4]);
+  for (int s = 0; s < h->prof_slot; ++s) profile_add(h, &h->evpool[(size_t)s * 5]);
+  h->prof_slot = 0;
+}
+// call after mark(4): folds the four intervals of one step into the totals (mode 1 synchronises the stream every step,
+// mode 2 only when its event pool is full)
+inline void profile_collect(bflbm_lattice* h) {
+  if (!h->profiling) return;
+  if (h->prof_deferred) {
+    if (++h->prof_slot == bflbm_lattice::PROF_POOL_STEPS) profile_flush(h);
+    return;
+  }
+  cudaEventSynchronize(h->ev[4]);
+  profile_add(h, h->ev);
 }
 
 int set_device(const bflbm_lattice* h) {
@@ -853,6 +874,7 @@ int bflbm_destroy(bflbm_lattice* h) {
   cudaFree(h->mailbox);
   cudaFree(h->stage); cudaFree(h->diag_partial); cudaFree(h->diag_count);
   for (int i = 0; i < 5; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -1451,9 +1473,16 @@ int bflbm_set_profiling(bflbm_lattice* h, int on) {
   CHECK_H(h);
   int rc = set_device(h);
   if (rc) return rc;
+  if (on < 0 || on > 2) return fail(BFLBM_ERR_ARG, "profiling mode must be 0 (off), 1 (read back every step) or 2 (deferred)");
   if (on && !h->ev[0])
     for (int i = 0; i < 5; ++i) CU(cudaEventCreate(&h->ev[i]));
+  if (on == 2 && h->evpool.empty()) {
+    h->evpool.resize((size_t)bflbm_lattice::PROF_POOL_STEPS * 5, nullptr);
+    for (cudaEvent_t& e : h->evpool) CU(cudaEventCreate(&e));
+  }
   h->profiling = on != 0;
+  h->prof_deferred = on == 2;
+  h->prof_slot = 0;
   for (int i = 0; i < 4; ++i) h->prof_ms[i] = 0.;
   h->prof_steps = 0;
   return 0;
@@ -1461,6 +1490,11 @@ int bflbm_set_profiling(bflbm_lattice* h, int on) {
 int bflbm_get_profile(bflbm_lattice* h, double ms4[4], long long* steps) {
   CHECK_H(h);
   if (!ms4) return fail(BFLBM_ERR_ARG, "null output");
+  if (h->prof_deferred) {
+    int rc = set_device(h);
+    if (rc) return rc;
+    profile_flush(h);
+  }
   for (int i = 0; i < 4; ++i) ms4[i] = h->prof_ms[i];
   if (steps) *steps = h->prof_steps;
   return 0;

@@ -384,8 +384,9 @@ class Lattice:
         _check(rc)
         return n.value
 
-    def set_profiling(self, on: bool):
-        _check(self.lib.bflbm_set_profiling(self.h, int(bool(on))))
+    def set_profiling(self, on):
+        """False/0 off, True/1 events read back after every step, 2 deferred read-back (no host synchronisation per step)"""
+        _check(self.lib.bflbm_set_profiling(self.h, int(on)))
 
     def profile(self):
         """(ms per step of {step kernel, density fold, halo pack, halo unpack}, steps accumulated)"""

@@ -256,7 +256,9 @@ const char* bflbm_multi_last_error(void);
 /* Per-kernel device timing (CUDA events on the lattice's stream around each launch of a step):
  * ms4 = accumulated milliseconds of {collide+stream kernel, density fold / density pass, halo pack, halo unpack},
  * steps = steps accumulated since profiling was switched on.  Off by default (events serialise nothing but
- * cost a little launch overhead). */
+ * cost a little launch overhead).  on = 1 reads the events back after every step (one host synchronisation per step);
+ * on = 2 defers the read-back to bflbm_get_profile (or every 128 steps): nothing but the event records enters a timed
+ * region.  While profiling is on, steps are plain launches (no graph replay) and slab steps run on one stream. */
 int bflbm_set_profiling(bflbm_lattice* h, int on);
 int bflbm_get_profile(bflbm_lattice* h, double ms4[4], long long* steps);
 

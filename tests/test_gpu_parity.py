@@ -589,3 +589,27 @@ def test_checker_is_pinned_to_reference_headers_on_this_box(oracle_mod):
     import test_oracle
     test_oracle.test_port_matches_reference_headers_bitwise(oracle_mod)
     test_oracle.test_port_reference_state_noise_matches_ref_build_bitwise(oracle_mod)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [1, 2])
+def test_profiled_steps_equal_plain_steps(bflbm, mode):
+    """bflbm_set_profiling: CUDA events around every launch (mode 2: read back on demand, 130 steps wrap the event pool once).
+    Timing must not change a bit of the result, and every step must be accounted for."""
+    shape = (24, 20, 16)
+    prm = bflbm.Params(kBT=1e-5, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, seed=11)
+    nsteps = 130
+    with make_lattice(bflbm, shape, prm, "fused") as A, make_lattice(bflbm, shape, prm, "fused") as B:
+        A.init_droplet(0.3)
+        B.init_droplet(0.3)
+        A.step(nsteps)
+        B.set_profiling(mode)
+        B.step(nsteps)
+        ms, n = B.profile()
+        B.set_profiling(0)
+        assert n == nsteps
+        assert ms[0] > 0 and ms[1] >= 0
+        assert np.array_equal(A.hydrovars(), B.hydrovars())
+        B.step(3)  # back to graph replay
+        A.step(3)
+        assert np.array_equal(A.hydrovars(), B.hydrovars())
