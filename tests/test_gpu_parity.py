@@ -597,7 +597,7 @@ def test_profiled_steps_equal_plain_steps(bflbm, mode):
     """bflbm_set_profiling: CUDA events around every launch (mode 2: read back on demand, 130 steps wrap the event pool once).
     Timing must not change a bit of the result, and every step must be accounted for."""
     shape = (24, 20, 16)
-    prm = bflbm.Params(kBT=1e-5, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, seed=11)
+    prm = dict(kBT=1e-5, alpha0=1.5, kappa=0.1, rho_lo=0.1, rho_hi=3.0, seed=11)
     nsteps = 130
     with make_lattice(bflbm, shape, prm, "fused") as A, make_lattice(bflbm, shape, prm, "fused") as B:
         A.init_droplet(0.3)
