@@ -95,6 +95,18 @@ struct bflbm_lattice {
   unsigned long long* diag_count = nullptr;
   size_t diag_blocks = 0;
 
+  // asynchronous host transfers (bflbm_stage_populations / bflbm_get_hydrovars*_async): a copy stream next to the lattice's
+  // stream, a checkpoint-sized staging area (`pre`) and an output buffer (`post`) on the device, all created on first use
+  cudaStream_t cpy = nullptr;
+  cudaEvent_t ev_staged = nullptr, ev_pre_free = nullptr, ev_observed = nullptr, ev_downloaded = nullptr;
+  double* pre = nullptr;
+  size_t pre_doubles = 0;
+  int pre_state = 0;           // 0 nothing staged, 1 plain arrays, 2 ghosted arrays
+  bool pre_consumed_once = false;
+  double* post = nullptr;
+  size_t post_doubles = 0;
+  bool download_pending = false;
+
   dim3 block, grid_xy;  // thread-per-cell kernels: grid = (grid_xy.x, grid_xy.y, planes)
 
   // CUDA graphs of K consecutive whole-box steps (launch-bound small lattices: Parameters:1-37 runs 32^3 .. 8x256x64 boxes
@@ -838,9 +850,136 @@ int observe_pair(bflbm_lattice* h, double* a, double* b, bool into_global) {
   CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
+
+// ---- asynchronous host transfers ------------------------------------------------------------------------------------------
+int ensure_copy_stream(bflbm_lattice* h) {
+  if (h->cpy) return 0;
+  CU(cudaStreamCreateWithFlags(&h->cpy, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&h->ev_staged, &h->ev_pre_free, &h->ev_observed, &h->ev_downloaded}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  return 0;
+}
+int ensure_buffer(bflbm_lattice* h, double** buf, size_t* have, size_t doubles) {
+  if (*have >= doubles) return 0;
+  if (*buf) {
+    CU(cudaStreamSynchronize(h->cpy));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaFree(*buf));
+    h->bytes -= *have * sizeof(double);
+    *buf = nullptr;
+    *have = 0;
+  }
+  CU(cudaMalloc((void**)buf, doubles * sizeof(double)));
+  *have = doubles;
+  h->bytes += doubles * sizeof(double);
+  return 0;
+}
+
+// observer over the whole local lattice into `post` (component-major = the host layout), then ONE device -> host copy on the
+// copy stream; steps queued on the lattice's stream afterwards run next to the copy
+template <int MODE>
+int observe_async(bflbm_lattice* h, int ncomp, double* out) {
+  CHECK_H(h);
+  if (!out) return fail(BFLBM_ERR_ARG, "null output buffer");
+  if (!h->initialized) return fail(BFLBM_ERR_STATE, "lattice not initialised");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = ensure_copy_stream(h))) return rc;
+  if ((rc = ensure_full_R(h))) return rc;
+  const Geom& G = h->G;
+  const size_t n = (size_t)ncomp * G.nzl * G.plane;
+  if ((rc = ensure_buffer(h, &h->post, &h->post_doubles, n))) return rc;
+  if (h->download_pending) CU(cudaStreamWaitEvent(h->stream, h->ev_downloaded, 0));  // `post` is still being read
+  if (h->prm.kBT > 0.) k_observe<MODE, true><<<cell_grid(h, G.nzl), h->block, 0, h->stream>>>(G, h->dp, h->step, 0, h->X[h->cur], h->R, h->post, rs_of(h));
+  else                 k_observe<MODE, false><<<cell_grid(h, G.nzl), h->block, 0, h->stream>>>(G, h->dp, h->step, 0, h->X[h->cur], h->R, h->post, rs_of(h));
+  ++h->launches;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(h->ev_observed, h->stream));
+  CU(cudaStreamWaitEvent(h->cpy, h->ev_observed, 0));
+  CU(cudaMemcpyAsync(out, h->post, n * sizeof(double), cudaMemcpyDeviceToHost, h->cpy));
+  CU(cudaEventRecord(h->ev_downloaded, h->cpy));
+  h->download_pending = true;
+  return 0;
+}
 }  // namespace
 
 extern "C" {
+
+int bflbm_stage_populations(bflbm_lattice* h, const double* f, const double* g, int ghosted) {
+  CHECK_H(h);
+  if (!f || !g) return fail(BFLBM_ERR_ARG, "null population buffer");
+  if (ghosted != 0 && ghosted != 1) return fail(BFLBM_ERR_ARG, "ghosted must be 0 or 1");
+  if (!ghosted && !h->whole_box) return fail(BFLBM_ERR_ARG, "slab lattices stage ghosted arrays (19, nz_local + 2, ny, nx)");
+  if (h->pre_state) return fail(BFLBM_ERR_STATE, "a staged checkpoint is waiting for bflbm_init_from_staged");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = ensure_copy_stream(h))) return rc;
+  const size_t n = (size_t)Q * (h->G.nzl + (ghosted ? 2 : 0)) * h->G.plane;  // doubles per species
+  if ((rc = ensure_buffer(h, &h->pre, &h->pre_doubles, 2 * n))) return rc;
+  if (h->pre_consumed_once) CU(cudaStreamWaitEvent(h->cpy, h->ev_pre_free, 0));  // the scatter of the previous checkpoint has read `pre`
+  CU(cudaMemcpyAsync(h->pre, f, n * sizeof(double), cudaMemcpyHostToDevice, h->cpy));
+  CU(cudaMemcpyAsync(h->pre + n, g, n * sizeof(double), cudaMemcpyHostToDevice, h->cpy));
+  CU(cudaEventRecord(h->ev_staged, h->cpy));
+  h->pre_state = ghosted ? 2 : 1;
+  return 0;
+}
+int bflbm_stage_wait(bflbm_lattice* h) {
+  CHECK_H(h);
+  if (!h->cpy) return 0;
+  int rc = set_device(h);
+  if (rc) return rc;
+  CU(cudaEventSynchronize(h->ev_staged));
+  return 0;
+}
+int bflbm_init_from_staged(bflbm_lattice* h) {
+  CHECK_H(h);
+  if (!h->pre_state) return fail(BFLBM_ERR_STATE, "bflbm_init_from_staged: nothing staged");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const bool ghosted = h->pre_state == 2;
+  const Geom& G = h->G;
+  CU(cudaStreamWaitEvent(h->stream, h->ev_staged, 0));
+  // the staging area holds [f | g], each (19, planes, ny, nx): the layout k_scatter_populations expects of a chunk of all planes
+  k_scatter_populations<<<cell_grid(h, G.nzl + (ghosted ? 2 : 0)), h->block, 0, h->stream>>>(G, ghosted ? -1 : 0, ghosted ? 0 : 1, h->pre, h->X[h->cur]);
+  ++h->launches;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(h->ev_pre_free, h->stream));
+  h->pre_consumed_once = true;
+  h->pre_state = 0;
+  if ((rc = finish_init(h))) return rc;
+  if (h->whole_box) {
+    if ((rc = bflbm_halo_refresh_begin(h))) return rc;
+    return bflbm_halo_refresh_end(h);
+  }
+  return 0;  // a slab: the caller runs the halo refresh next, as after bflbm_init_from_populations_slab
+}
+int bflbm_get_hydrovars_async(bflbm_lattice* h, double* out22) { return observe_async<OBS_HYDRO>(h, BFLBM_NHYDRO, out22); }
+int bflbm_get_hydrovars_bar_async(bflbm_lattice* h, double* out9) { return observe_async<OBS_HBAR>(h, BFLBM_NHYDRO_BAR, out9); }
+int bflbm_download_wait(bflbm_lattice* h) {
+  CHECK_H(h);
+  if (!h->download_pending) return 0;
+  int rc = set_device(h);
+  if (rc) return rc;
+  CU(cudaEventSynchronize(h->ev_downloaded));
+  h->download_pending = false;
+  return 0;
+}
+int bflbm_release_staging(bflbm_lattice* h) {
+  CHECK_H(h);
+  if (!h->cpy) return 0;
+  int rc = set_device(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->cpy));
+  CU(cudaStreamSynchronize(h->stream));
+  h->download_pending = false;
+  h->pre_state = 0;
+  h->pre_consumed_once = false;
+  CU(cudaFree(h->pre));
+  CU(cudaFree(h->post));
+  h->bytes -= (h->pre_doubles + h->post_doubles) * sizeof(double);
+  h->pre = h->post = nullptr;
+  h->pre_doubles = h->post_doubles = 0;
+  return 0;
+}
 
 int bflbm_params_default(bflbm_params* p) {
   if (!p) return fail(BFLBM_ERR_ARG, "null params");
@@ -873,6 +1012,9 @@ int bflbm_destroy(bflbm_lattice* h) {
   release_ipc(h);
   cudaFree(h->mailbox);
   cudaFree(h->stage); cudaFree(h->diag_partial); cudaFree(h->diag_count);
+  if (h->cpy) { cudaStreamSynchronize(h->cpy); cudaStreamDestroy(h->cpy); }
+  for (cudaEvent_t e : {h->ev_staged, h->ev_pre_free, h->ev_observed, h->ev_downloaded}) if (e) cudaEventDestroy(e);
+  cudaFree(h->pre); cudaFree(h->post);
   for (int i = 0; i < 5; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

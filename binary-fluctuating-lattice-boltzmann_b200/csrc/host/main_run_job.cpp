@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
+#include <memory>
 #include <sstream>
 
 #include "../../../include/bflbm_sf.h"
@@ -114,10 +115,14 @@ int main(int argc, char** argv) {
     MultiFabNANCheck(L);  // main_run_job.cpp:294-297 (throws instead of exit(0))
 
     const bool plot_real = R.plot_fields == "hydrovars";
-    auto write_output = [&](int step) {  // WriteOutput, main_run_job.cpp:35-55
+    // WriteOutput, main_run_job.cpp:35-55.  The frame is downloaded here; the file is written by the writer thread while the
+    // main thread queues the next interval's steps (async_output = 0: inline, like the reference)
+    FrameWriter writer(R.async_output);
+    auto write_output = [&](int step) {
       const std::string dir = concatenate(plot_file_root, step, R.Ndigits);
-      if (plot_real) write_plotfile(dir, L.hydrovars(), BFLBM_NHYDRO, nx, ny, nz, VariableNames(BFLBM_NHYDRO), step, step);
-      else           write_plotfile(dir, L.hydrovars_bar(), BFLBM_NHYDRO_BAR, nx, ny, nz, VariableNames(BFLBM_NHYDRO_BAR), step, step);
+      const int nc = plot_real ? BFLBM_NHYDRO : BFLBM_NHYDRO_BAR;
+      auto frame = std::make_shared<std::vector<double>>(plot_real ? L.hydrovars() : L.hydrovars_bar());
+      writer.push([=] { write_plotfile(dir, *frame, nc, nx, ny, nz, VariableNames(nc), step, step); });
     };
     if (R.plot_int > 0 && R.step_continue == 0) write_output(0);
     std::printf("LB initialized with alpha0 = %g and T = %g\n", R.alpha0, R.kBT);
@@ -153,11 +158,14 @@ int main(int argc, char** argv) {
         throw std::runtime_error("structure-factor accumulator: accumulate failed");
       if (R.print_int > 0 && step % R.print_int == 0) std::printf("LB step %d info:\n", step);
       if (noiseSwitch && R.out_noise_step > 0 && step % R.out_noise_step == 0) {  // WriteOutNoise, Debug.H:380-409
-        auto nz2 = L.noise();
+        auto nz2 = std::make_shared<std::pair<std::vector<double>, std::vector<double>>>(L.noise());
         std::vector<std::string> fa, ga;
         for (int a = 0; a < BFLBM_NVEL; ++a) { fa.push_back("fa" + std::to_string(a)); ga.push_back("ga" + std::to_string(a)); }
-        write_plotfile(concatenate(plot_file_root + "_fnoise", step, R.Ndigits), nz2.first, BFLBM_NVEL, nx, ny, nz, fa, step, step);
-        write_plotfile(concatenate(plot_file_root + "_gnoise", step, R.Ndigits), nz2.second, BFLBM_NVEL, nx, ny, nz, ga, step, step);
+        const std::string fdir = concatenate(plot_file_root + "_fnoise", step, R.Ndigits), gdir = concatenate(plot_file_root + "_gnoise", step, R.Ndigits);
+        writer.push([=] {
+          write_plotfile(fdir, nz2->first, BFLBM_NVEL, nx, ny, nz, fa, step, step);
+          write_plotfile(gdir, nz2->second, BFLBM_NVEL, nx, ny, nz, ga, step, step);
+        });
       }
       if (R.plot_int > 0 && step % R.plot_int == 0) {
         std::printf("\t**************************************\t\n\tLB step %d & Output\n\t**************************************\t\n", step);
@@ -192,6 +200,7 @@ int main(int argc, char** argv) {
     }
     if (structFact) bflbm_sf_destroy(structFact);
     L.sync();
+    writer.drain();  // every frame is on disk (the equilibrium extraction below reads them back)
     const double loop_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
 
     // ---- checkpoint, main_run_job.cpp:398-409 ---------------------------------------------------------------------

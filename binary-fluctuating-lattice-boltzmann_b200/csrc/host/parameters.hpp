@@ -41,6 +41,8 @@ struct RunParameters {
   int device = 0;
   int ngpus = 1;     // z-slabs over devices device .. device+ngpus-1 of this process (the reference: mpirun ranks + max_grid_size)
   int brick_lz = 0;  // brick height of the step kernel; 0 = automatic.  Same value => same bits on any GPU count
+  int async_output = 2;  // frames waiting for the writer thread (plotfiles are written while the GPUs run the next interval);
+                         // 0 = write inline like the reference (main_run_job.cpp:372-385)
   // LBM_d3q19.H:10, LBM_binary.H:17-30
   double kBT = 0., tau_f = 0.5, tau_g = 0.5, alpha0 = 4., alpha1 = 0., kappa = 4., rho_lo = 0., rho_hi = 1.;
   unsigned long long seed = 12345ull;
@@ -99,7 +101,7 @@ inline RunParameters parse_parameters(std::istream& in) {
   P_INT(step_continue); P_BOOL(continueFromNonFluct); P_BOOL(if_continue_from_last_frame);
   P_INT(nsteps); P_INT(out_step); P_INT(plot_int); P_INT(print_int); P_INT(t_window); P_INT(out_noise_step);
   P_INT(plot_SF_window); P_INT(out_SF_step);
-  P_DBL(radius); P_BOOL(if_print_radius); P_DBL(init_frac); P_STR(root_path); P_INT(Ndigits); P_STR(plot_fields); P_INT(device); P_INT(ngpus); P_INT(brick_lz);
+  P_DBL(radius); P_BOOL(if_print_radius); P_DBL(init_frac); P_STR(root_path); P_INT(Ndigits); P_STR(plot_fields); P_INT(device); P_INT(ngpus); P_INT(brick_lz); P_INT(async_output);
   P_DBL(kBT); P_DBL(tau_f); P_DBL(tau_g); P_DBL(alpha0); P_DBL(alpha1); P_DBL(kappa); P_DBL(rho_lo); P_DBL(rho_hi);
   take("seed", [&](const std::string& v) { P.seed = std::stoull(v); });
   P_BOOL(use_ref_state); P_BOOL(use_SC_pseudo); P_DBL(SC_ref_density);
@@ -113,6 +115,7 @@ inline RunParameters parse_parameters(std::istream& in) {
   if (P.use_SC_pseudo) throw std::runtime_error("Parameters: use_SC_pseudo = true is a dead branch in the reference and is not supported");
   if (P.plot_fields != "hydrovars" && P.plot_fields != "hydrovars_bar") throw std::runtime_error("Parameters: plot_fields must be hydrovars | hydrovars_bar");
   if (P.ngpus < 1) throw std::runtime_error("Parameters: ngpus must be >= 1");
+  if (P.async_output < 0) throw std::runtime_error("Parameters: async_output must be >= 0");
   if (P.ny <= 0) P.ny = P.nx;
   if (P.nz <= 0) P.nz = P.nx;
   if (P.t_window < 0) P.t_window = 5 * P.plot_int;

@@ -9,6 +9,12 @@
 
 #include <algorithm>
 #include <cerrno>
+#include <condition_variable>
+#include <deque>
+#include <exception>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -217,5 +223,76 @@ inline PlotfileData read_plotfile(const std::string& dir) {
   if (covered < n) throw std::runtime_error(dir + ": the FABs do not cover the domain");
   return P;
 }
+
+// Output off the critical path.  The reference writes every frame inline between two time steps (WriteOutput,
+// main_run_job.cpp:372-385); at the reference's own job sizes a frame costs more host time than the steps between two
+// frames cost GPU time.  Here the driver hands the downloaded frame to ONE writer thread and goes on queueing steps; at most
+// `max_pending` frames wait (that bounds the host memory), push() blocks beyond that.  max_pending = 0: write inline.
+// drain() returns when everything is on disk and rethrows the first error of the writer.
+class FrameWriter {
+ public:
+  explicit FrameWriter(int max_pending) : max_pending_(max_pending) {
+    if (max_pending_ > 0) worker_ = std::thread([this] { run(); });
+  }
+  ~FrameWriter() {
+    try { drain(); } catch (...) {}
+    if (worker_.joinable()) {
+      { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+      cv_.notify_all();
+      worker_.join();
+    }
+  }
+  FrameWriter(const FrameWriter&) = delete;
+  FrameWriter& operator=(const FrameWriter&) = delete;
+
+  void push(std::function<void()> job) {
+    if (max_pending_ <= 0) { job(); return; }
+    std::unique_lock<std::mutex> g(m_);
+    cv_.wait(g, [&] { return (int)q_.size() < max_pending_ || err_; });
+    if (err_) { auto e = err_; err_ = nullptr; std::rethrow_exception(e); }
+    q_.push_back(std::move(job));
+    ++written_async_;
+    g.unlock();
+    cv_.notify_all();
+  }
+  void drain() {
+    if (max_pending_ <= 0) return;
+    std::unique_lock<std::mutex> g(m_);
+    cv_.wait(g, [&] { return (q_.empty() && !busy_) || err_; });
+    if (err_) { auto e = err_; err_ = nullptr; std::rethrow_exception(e); }
+  }
+  long long frames_written_async() const { return written_async_; }
+
+ private:
+  void run() {
+    for (;;) {
+      std::function<void()> job;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return stop_ || !q_.empty(); });
+        if (q_.empty()) return;
+        job = std::move(q_.front());
+        q_.pop_front();
+        busy_ = true;
+      }
+      std::exception_ptr e;
+      try { job(); } catch (...) { e = std::current_exception(); }
+      {
+        std::lock_guard<std::mutex> g(m_);
+        busy_ = false;
+        if (e && !err_) err_ = e;
+      }
+      cv_.notify_all();
+    }
+  }
+  int max_pending_;
+  std::thread worker_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::deque<std::function<void()>> q_;
+  bool stop_ = false, busy_ = false;
+  std::exception_ptr err_;
+  long long written_async_ = 0;
+};
 
 }  // namespace bflbm

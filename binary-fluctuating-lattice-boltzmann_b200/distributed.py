@@ -222,6 +222,13 @@ class SlabLattice:
         self._exchange()
         _check(self.lat.lib.bflbm_halo_refresh_end(self.lat.h))
 
+    def init_from_staged(self):
+        """The staged (ghosted) checkpoint of this slab + the halo refresh: init_from_populations_slab without the host."""
+        self.lat.init_from_staged()
+        _check(self.lat.lib.bflbm_halo_refresh_begin(self.lat.h))
+        self._exchange()
+        _check(self.lat.lib.bflbm_halo_refresh_end(self.lat.h))
+
     def init_from_global_populations(self, f, g):
         """Convenience for tests: every rank passes the WHOLE box (19, nz, ny, nx) and keeps its slab + ghost planes."""
         idx = [(z % self.nz_global) for z in range(self.z0 - 1, self.z0 + self.nzl + 1)]
@@ -237,16 +244,14 @@ class SlabLattice:
             self._exchange()
             _check(lib.bflbm_step_end(h))
 
-    def run_e2e(self, nsteps, out_pinned, pinned):
-        """bench.py helper: restart upload + nsteps + hydrovsbar download on this slab, host buffers."""
-        import time
+    def host_checkpoint(self):
+        """bench.py helper (untimed): this slab's populations as a ghosted host checkpoint, (2, 19, nz_local + 2, ny, nx), pinned
+        if the host allows it.  The ghost planes come from the ring neighbours once, here -- like reading a checkpoint file
+        that already has them."""
         import torch
-        import torch.distributed as dist
         lat = self.lat
-        f, g = lat.populations()  # untimed: makes the host checkpoint of this slab
-        # ghost planes of the host checkpoint come from the ring neighbours (host-side exchange through the GPUs' path
-        # would hide the cost, so it is done here once, untimed, like reading a checkpoint file that already has them)
-        try:  # pinned host checkpoint, like the single-GPU leg
+        f, g = lat.populations()
+        try:
             fg = torch.empty((2, NVEL, self.nzl + 2, lat.ny, lat.nx), dtype=torch.float64, pin_memory=True).numpy()
         except Exception:
             fg = np.empty((2, NVEL, self.nzl + 2, lat.ny, lat.nx))
@@ -259,24 +264,4 @@ class SlabLattice:
         fg[:, :, 0] = lo_recv.cpu().numpy()
         fg[:, :, -1] = hi_recv.cpu().numpy()
         torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        self.init_from_populations_slab(fg[0], fg[1])
-        t1 = time.perf_counter()
-        self.step(nsteps)
-        _check(lat.lib.bflbm_sync(lat.h))
-        t2 = time.perf_counter()
-        _check(lat.lib.bflbm_get_hydrovars_bar(lat.h, out_pinned.numpy().ctypes.data))
-        torch.cuda.synchronize()
-        t3 = time.perf_counter()
-        ph = torch.tensor([t3 - t0, t1 - t0, t2 - t1, t3 - t2], device=self.device, dtype=torch.float64)
-        dist.all_reduce(ph, op=dist.ReduceOp.MAX)  # slowest rank per phase; the interval is the slowest rank's total
-        dt, up, st, down = (float(v) for v in ph.tolist())
-        cells_local = self.nzl * lat.ny * lat.nx
-        cells = lat.nx * lat.ny * self.nz_global
-        return {"value": cells * nsteps / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 2 * 19 * 8 * (cells_local + 2 * lat.ny * lat.nx) / nsteps,
-                "d2h_bytes_per_step": 9 * 8 * cells_local / nsteps, "steps_per_interval": nsteps, "seconds": dt, "pinned_host": pinned,
-                "phases_s": {"upload": up, "steps": st, "download": down},
-                "h2d_gb_per_s_per_gpu": 2 * 19 * 8 * (cells_local + 2 * lat.ny * lat.nx) / up / 1e9,
-                "what": "per rank: bflbm_init_from_populations_slab(host f,g) + halo refresh + nsteps x (step_begin, NCCL ring exchange, "
-                        "step_end) + bflbm_get_hydrovars_bar(host); wall clock, max over ranks"}
+        return fg

@@ -18,6 +18,6 @@ def build(force: bool = False) -> str:
     if not force and os.path.exists(EXE) and all(os.path.getmtime(d) <= os.path.getmtime(EXE) for d in deps):
         return EXE
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", SRC, "-o", EXE, "-L" + HERE, "-lbflbm_sf", "-lbflbm", "-Wl,-rpath,$ORIGIN",
+    subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", "-pthread", SRC, "-o", EXE, "-L" + HERE, "-lbflbm_sf", "-lbflbm", "-Wl,-rpath,$ORIGIN",
                     "-Wl,-rpath-link," + HERE, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
     return EXE

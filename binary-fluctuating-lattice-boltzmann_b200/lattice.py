@@ -84,6 +84,13 @@ def load_library() -> ctypes.CDLL:
         "bflbm_init_droplet": (ip, [vp, dp]),
         "bflbm_init_from_populations": (ip, [vp, vp, vp]),
         "bflbm_init_from_populations_slab": (ip, [vp, vp, vp]),
+        "bflbm_stage_populations": (ip, [vp, vp, vp, ip]),
+        "bflbm_stage_wait": (ip, [vp]),
+        "bflbm_init_from_staged": (ip, [vp]),
+        "bflbm_get_hydrovars_async": (ip, [vp, vp]),
+        "bflbm_get_hydrovars_bar_async": (ip, [vp, vp]),
+        "bflbm_download_wait": (ip, [vp]),
+        "bflbm_release_staging": (ip, [vp]),
         "bflbm_step": (ip, [vp, ip]),
         "bflbm_sync": (ip, [vp]),
         "bflbm_step_count": (ctypes.c_longlong, [vp]),
@@ -205,6 +212,8 @@ class Lattice:
             _check(self.lib.bflbm_create_slab(ctypes.byref(cp), self.nx, self.ny, self.nz_global, self.z0, self.nz,
                                               device, ctypes.byref(h)))
         self.h = h
+        self._staged_refs = None   # host arrays of transfers in flight are kept alive here
+        self._download_ref = None
 
     # -- lifetime ---------------------------------------------------------------------------------
     def close(self):
@@ -262,6 +271,52 @@ class Lattice:
         f = _host(f_ghosted, shp, "f_ghosted")
         g = _host(g_ghosted, shp, "g_ghosted")
         _check(self.lib.bflbm_init_from_populations_slab(self.h, f.ctypes.data, g.ctypes.data))
+
+    # -- asynchronous host transfers (include/bflbm.h "asynchronous host transfers") -----------------------------------
+    def stage_populations(self, f, g, ghosted=False):
+        """Start the host -> device copy of a checkpoint next to whatever the lattice is doing.  The arrays are used in place
+        (no conversion copy): they must be C-contiguous float64 of the right shape and stay alive and untouched until
+        stage_wait() (pinned memory, e.g. torch.empty(..., pin_memory=True).numpy(), makes the copy asynchronous)."""
+        shp = (NVEL, self.nz + (2 if ghosted else 0), self.ny, self.nx)
+        for a, name in ((f, "f"), (g, "g")):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.shape == shp):
+                raise ValueError(f"{name}: need a C-contiguous float64 array of shape {shp}")
+        _check(self.lib.bflbm_stage_populations(self.h, f.ctypes.data, g.ctypes.data, 1 if ghosted else 0))
+        self._staged_refs = (f, g)
+
+    def stage_wait(self):
+        _check(self.lib.bflbm_stage_wait(self.h))
+        self._staged_refs = None
+
+    def init_from_staged(self):
+        """init_from_populations[_slab] of the staged checkpoint, queued behind the copy on the lattice's stream."""
+        _check(self.lib.bflbm_init_from_staged(self.h))
+
+    def hydrovars_bar_async(self, out=None):
+        """Observer now, device -> host copy next to the following steps; `out` is complete after download_wait()."""
+        if out is None:
+            out = np.empty((NHYDRO_BAR,) + self.shape)
+        if not (out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (NHYDRO_BAR,) + self.shape):
+            raise ValueError("out: need a C-contiguous float64 array of shape %r" % (((NHYDRO_BAR,) + self.shape),))
+        _check(self.lib.bflbm_get_hydrovars_bar_async(self.h, out.ctypes.data))
+        self._download_ref = out
+        return out
+
+    def hydrovars_async(self, out=None):
+        if out is None:
+            out = np.empty((NHYDRO,) + self.shape)
+        if not (out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (NHYDRO,) + self.shape):
+            raise ValueError("out: need a C-contiguous float64 array of shape %r" % (((NHYDRO,) + self.shape),))
+        _check(self.lib.bflbm_get_hydrovars_async(self.h, out.ctypes.data))
+        self._download_ref = out
+        return out
+
+    def download_wait(self):
+        _check(self.lib.bflbm_download_wait(self.h))
+        self._download_ref = None
+
+    def release_staging(self):
+        _check(self.lib.bflbm_release_staging(self.h))
 
     def init_from_global_populations(self, f_global, g_global):
         """Host arrays of the WHOLE box (19, nz_global, ny, nx); a slab takes its planes and the periodic neighbour planes."""

@@ -148,6 +148,30 @@ int bflbm_get_hydrovars_into_global(bflbm_lattice* h, double* global22);
 int bflbm_get_hydrovars_bar_into_global(bflbm_lattice* h, double* global9);
 int bflbm_get_noise_into_global(bflbm_lattice* h, double* fn_global, double* gn_global);
 
+/* ---- asynchronous host transfers: ensembles of restarts and output while stepping ----------------------------------------
+ * The reference's two-stage workflow starts every fluctuating run from the checkpoint of the kBT = 0 run
+ * (LoadSingleMultiFab + LBM_init, main_run_job.cpp:244-268) and writes a frame every plot_int steps (:372-385).  With the calls above both transfers
+ * stand between the steps.  These move them next to the steps, on a copy stream of the lattice:
+ *   bflbm_stage_populations : starts the host -> device copy of a checkpoint into a staging area on the device and returns at
+ *       once; the lattice may be stepping meanwhile.  ghosted = 0: arrays (19, nz_local, ny, nx), whole box (the arguments of
+ *       bflbm_init_from_populations); ghosted = 1: (19, nz_local + 2, ny, nx) (those of bflbm_init_from_populations_slab).
+ *       The host arrays must stay untouched until bflbm_stage_wait (or bflbm_init_from_staged + bflbm_sync) has returned;
+ *       pinned host memory makes the copy truly asynchronous.  One checkpoint can be staged at a time.
+ *   bflbm_init_from_staged  : bflbm_init_from_populations[_slab] of the staged checkpoint, bit for bit, queued on the lattice's
+ *       stream behind the copy (no host synchronisation).  Consumes the staged checkpoint; the next one may be staged at once.
+ *   bflbm_get_hydrovars_async / _bar_async : the observer runs on the lattice's stream into a device buffer, the device -> host
+ *       copy on the copy stream; returns at once, steps queued afterwards overlap the copy.  The host array is complete
+ *       after bflbm_download_wait.  One download in flight per lattice (a second call waits for the first on the device).
+ * Device memory: the staging area (2 x 19 doubles per cell) and the output buffer (9 or 22 per cell) are allocated on first
+ * use and kept; bflbm_release_staging frees them. */
+int bflbm_stage_populations(bflbm_lattice* h, const double* f, const double* g, int ghosted);
+int bflbm_stage_wait(bflbm_lattice* h);
+int bflbm_init_from_staged(bflbm_lattice* h);
+int bflbm_get_hydrovars_async(bflbm_lattice* h, double* out22);
+int bflbm_get_hydrovars_bar_async(bflbm_lattice* h, double* out9);
+int bflbm_download_wait(bflbm_lattice* h);
+int bflbm_release_staging(bflbm_lattice* h);
+
 /* update_com  LBM_hydrovs.H:26-60 (centre of mass of rho; local-slab partial sums:
  * sums4 = {mass, sum rho*x, sum rho*y, sum rho*z_global}). */
 int bflbm_center_of_mass(bflbm_lattice* h, double* com3, double* sums4);

@@ -63,6 +63,39 @@ int main(int argc, char** argv) {
     assert(M.nboxes == 12 && M.nx == nx && M.ny == ny && M.nz == nz && M.step == 7);
     assert(M.data == d);
   }
+  {  // FrameWriter: jobs run in order on the writer thread, at most max_pending wait, errors come back to the caller
+    std::vector<int> order;
+    {
+      FrameWriter w(2);
+      for (int i = 0; i < 20; ++i) w.push([&order, i] { order.push_back(i); });
+      w.drain();
+      assert(order.size() == 20 && w.frames_written_async() == 20);
+      for (int i = 0; i < 20; ++i) assert(order[i] == i);
+      w.push([] { throw std::runtime_error("disk full"); });
+      bool thrown = false;
+      try { w.drain(); } catch (const std::runtime_error& e) { thrown = std::string(e.what()) == "disk full"; }
+      assert(thrown);
+      w.push([&order] { order.push_back(99); });  // usable again after the error was reported
+      w.drain();
+      assert(order.back() == 99);
+    }
+    FrameWriter inline_writer(0);  // async_output = 0: the job runs in the caller
+    bool ran = false;
+    inline_writer.push([&ran] { ran = true; });
+    assert(ran && inline_writer.frames_written_async() == 0);
+    // files written through the writer are the files written inline
+    const int nx = 4, ny = 3, nz = 2;
+    std::vector<double> d((size_t)nx * ny * nz * 9);
+    for (size_t i = 0; i < d.size(); ++i) d[i] = 0.5 * (double)i;
+    {
+      FrameWriter w(1);
+      for (int s = 0; s < 3; ++s) w.push([=] { write_plotfile(concatenate(tmp + "/bflbm_async_plt", s, 7), d, 9, nx, ny, nz, {"a"}, s, s); });
+    }  // the destructor drains
+    for (int s = 0; s < 3; ++s) assert(read_plotfile(concatenate(tmp + "/bflbm_async_plt", s, 7)).data == d);
+    { std::istringstream in("async_output = 0\n"); assert(parse_parameters(in).async_output == 0); }
+    { std::istringstream in("async_output = -1\n"); EXPECT_THROW(parse_parameters(in)); }
+    { std::istringstream in(""); assert(parse_parameters(in).async_output == 2); }
+  }
   std::puts("host_cpp_test ok");
   return 0;
 }

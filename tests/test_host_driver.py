@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_host_cpp_parser_and_plotfile(tmp_path):
     exe = tmp_path / "host_cpp_test"
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-std=c++17", "-O1", os.path.join(ROOT, "tests", "host_cpp_test.cpp"), "-o", str(exe)], check=True)
+    subprocess.run([cxx, "-std=c++17", "-O1", "-pthread", os.path.join(ROOT, "tests", "host_cpp_test.cpp"), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe), str(tmp_path)], check=True, capture_output=True, text=True).stdout
     assert "host_cpp_test ok" in out
 
