@@ -290,7 +290,7 @@ def run_b200(a):
     # no host synchronisation per step).  Event records make the steps plain launches instead of graph replays and put a
     # slab step on one stream, so they go INTO the timed region only where that costs nothing: one GPU, steps of
     # milliseconds.  Small boxes and slabs are timed undisturbed and profiled in a second pass of the same K steps.
-    profile_in_timed = world == 1 and cells_local_hint(a, nzl) >= (1 << 24)
+    profile_in_timed = world == 1 and cells_local_hint(a, nzl) >= (1 << 24) and os.environ.get("BFLBM_BENCH_PROFILE_IN_TIMED", "1") != "0"
     if profile_in_timed:
         lat.set_profiling(2)
         barrier()

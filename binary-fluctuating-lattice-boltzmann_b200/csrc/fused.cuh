@@ -49,12 +49,6 @@
 #ifndef BFLBM_F_NORMALS_EARLY
 #define BFLBM_F_NORMALS_EARLY 0
 #endif
-#ifndef BFLBM_REREAD_CHUNK       // > 0: the second fetch goes in groups of this many loads, each group's addresses made to depend on
-#define BFLBM_REREAD_CHUNK 0     //      the previous group's results (bounds the loads in flight, i.e. the registers, of the epilogue)
-#endif
-#ifndef BFLBM_GENERAL_REREAD     // 1: general rates run the rate-1 schedule (nothing kept, nothing parked, all normals in the load
-#define BFLBM_GENERAL_REREAD 0   //    shadow) and fetch the old populations a SECOND time -- an L2 hit -- for the (1 - w) f_old term
-#endif
 
 namespace bflbm {
 
@@ -102,7 +96,7 @@ inline size_t brick_doubles2(const BrickGrid& B) { return (size_t)B.brick * B.bx
 constexpr int FIX_SLOTS = 200;  // extra contributions of one extended plane: 2*(ex + ey) + 4*12 - ... <= 192 for ex*ey <= 2*NT
 inline size_t fused_smem_bytes(const BrickGrid& B, bool rate1, bool noise) {
   return (size_t)7 * B.pl * sizeof(double2) + (size_t)B.pl * sizeof(int4) + (size_t)FIX_SLOTS * sizeof(double2) +
-         ((rate1 || BFLBM_GENERAL_REREAD) ? 0 : (size_t)((BFLBM_G_MOMENT_SPACE ? 15 : BFLBM_PARK_G) + BFLBM_PARK_F) * B.tx * B.ty * sizeof(double)) +
+         (rate1 ? 0 : (size_t)((BFLBM_G_MOMENT_SPACE ? 15 : BFLBM_PARK_G) + BFLBM_PARK_F) * B.tx * B.ty * sizeof(double)) +
          ((BFLBM_TRIG_TABLE && noise) ? (size_t)1024 * sizeof(float2) : 0);
 }
 // fold-in-staging (the step kernel sums the brick contributions itself) needs every cell to lie in at most
@@ -223,16 +217,14 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
   const float2* Trig = nullptr;
   constexpr bool TAB = NOISE && BFLBM_TRIG_TABLE;
   if (TAB) {
-    float2* t = reinterpret_cast<float2*>(So + ((RATE1 || BFLBM_GENERAL_REREAD) ? 0 : ((BFLBM_G_MOMENT_SPACE ? 15 : BFLBM_PARK_G) + BFLBM_PARK_F) * NT));
+    float2* t = reinterpret_cast<float2*>(So + (RATE1 ? 0 : ((BFLBM_G_MOMENT_SPACE ? 15 : BFLBM_PARK_G) + BFLBM_PARK_F) * NT));
     fill_trig_table(t, threadIdx.y * B.tx + threadIdx.x, NT);
     Trig = t;
   }
   // rate-1 kernels make all 33 normals in the load shadow; the general kernels (19 more live doubles) make g's 15 late
   constexpr int PARK_F = BFLBM_PARK_F, PARK_G = BFLBM_PARK_G;
-  constexpr bool REREAD = !RATE1 && BFLBM_GENERAL_REREAD;  // general rates on the rate-1 schedule + second fetch of the old populations
-  constexpr bool LIKE_R1 = RATE1 || REREAD;
-  constexpr bool FMA_NOISE = LIKE_R1 || BFLBM_GENERAL_FMA_NOISE;  // how the noise is applied (philox.cuh)
-  constexpr bool G_NORMALS_EARLY = LIKE_R1 || BFLBM_G_NORMALS_EARLY, F_NORMALS_EARLY = LIKE_R1 || BFLBM_F_NORMALS_EARLY;
+  constexpr bool FMA_NOISE = RATE1 || BFLBM_GENERAL_FMA_NOISE;  // how the noise is applied (philox.cuh)
+  constexpr bool G_NORMALS_EARLY = RATE1 || BFLBM_G_NORMALS_EARLY, F_NORMALS_EARLY = RATE1 || BFLBM_F_NORMALS_EARLY;
   __shared__ int nfix;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * B.tx + tx;
   const int x0 = blockIdx.x * B.tx, y0 = blockIdx.y * B.ty, zb = bZ * B.lz;
@@ -422,11 +414,11 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
           // in their shadow, before the first loaded value is touched
 #pragma unroll
           for (int i = 0; i < Q; ++i) go[i] = ld_off(XB.in[Q + i], off[i]);
-          if (LIKE_R1 || !BFLBM_GENERAL_SEQ) {
+          if (RATE1 || !BFLBM_GENERAL_SEQ) {
 #pragma unroll
             for (int i = 0; i < Q; ++i) fo[i] = ld_off(XB.in[i], off[i]);
           }
-          constexpr bool Y3_LATE = !LIKE_R1 && BFLBM_Y3_LATE;
+          constexpr bool Y3_LATE = !RATE1 && BFLBM_Y3_LATE;
           if (!Y3_LATE) {
             nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
             momentum_normals<NOISE, TAB>(nk, y3, Trig);
@@ -436,7 +428,7 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
           // only the conserved moments (density, momentum) of the incoming state are needed (physics.cuh, collide_species):
           // the rest of the forward transform is dead code
           moments(go, mg);
-          if (!LIKE_R1) {  // general rates: the incoming state of g waits in shared memory while f is processed
+          if (!RATE1) {  // general rates: the incoming state of g waits in shared memory while f is processed
             if (BFLBM_G_MOMENT_SPACE) {
 #pragma unroll
               for (int a = 4; a < Q; ++a) So[(a - 4) * NT + tid] = mg[a];
@@ -447,7 +439,7 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
               for (int i = PARK_G; i < Q; ++i) gk[i - PARK_G] = go[i];
             }
           }
-          if (!LIKE_R1 && BFLBM_GENERAL_SEQ) {
+          if (!RATE1 && BFLBM_GENERAL_SEQ) {
 #pragma unroll
             for (int i = 0; i < Q; ++i) fo[i] = ld_off(XB.in[i], off[i]);
           }
@@ -456,40 +448,21 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
             nk = make_noise_key(P.keys, (unsigned long long)cell_global(G, x, y, zl), step);
             momentum_normals<NOISE, TAB>(nk, y3, Trig);
           }
-          if (!LIKE_R1) {  // ... and so do the first PARK_F incoming populations of f (register pressure at the inverse transform)
+          if (!RATE1) {  // ... and so do the first PARK_F incoming populations of f (register pressure at the inverse transform)
 #pragma unroll
             for (int i = 0; i < PARK_F; ++i) So[(PARK_G + i) * NT + tid] = fo[i];
           }
         }
         collide_prepare<NOISE, FMA_NOISE>(P, grho, gphi, y3, mf, mg, C);
         if (!F_NORMALS_EARLY) mode_normals<NOISE, 0, TAB>(nk, ybf, Trig);
-        collide_species<NOISE, 0, RATE1, !LIKE_R1 && BFLBM_F_MOMENT_SPACE, FMA_NOISE>(P, ybf, C, mf);
+        collide_species<NOISE, 0, RATE1, !RATE1 && BFLBM_F_MOMENT_SPACE, FMA_NOISE>(P, ybf, C, mf);
       } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) mf[i] = fo[i] = 0.;
       }
-      // REREAD: the pull sources once more (byte offsets recomputed from the loop invariants: 19 live registers less)
-      auto pull_off = [&](int i) {
-        unsigned o = c;
-        if (cz(i) != 0) o += cz(i) > 0 ? 0u - pl8 : pl8;
-        if (cy(i) != 0) o += dyv[(1 + cy(i)) >> 1];
-        if (cx(i) != 0) o += dxv[(1 + cx(i)) >> 1];
-        return o;
-      };
       double p[Q];
       populations(mf, p);
-      // a zero the compiler cannot see through: makes the next group's addresses wait for this group's results
-      auto token = [](double v) { unsigned z; asm("and.b32 %0, %1, 0;" : "=r"(z) : "r"(__double2hiint(v))); return z; };
-      if (REREAD && active) {
-        const double kf = keep_of(P, 0);
-        unsigned tok = 0;
-#pragma unroll
-        for (int i = 0; i < Q; ++i) {
-          p[i] = fma(kf, ld_off(XB.in[i], pull_off(i) + tok), p[i]);
-          if (BFLBM_REREAD_CHUNK > 0 && (i + 1) % (BFLBM_REREAD_CHUNK > 0 ? BFLBM_REREAD_CHUNK : 1) == 0) tok = token(p[i]);
-        }
-      }
-      if (!LIKE_R1 && !BFLBM_F_MOMENT_SPACE) {
+      if (!RATE1 && !BFLBM_F_MOMENT_SPACE) {
         const double kf = keep_of(P, 0);
 #pragma unroll
         for (int i = 0; i < Q; ++i) p[i] = fma(kf, (i < PARK_F && active) ? So[(PARK_G + i) * NT + tid] : fo[i], p[i]);
@@ -503,27 +476,18 @@ k_step_fused(const __grid_constant__ Geom G, const __grid_constant__ BrickGrid B
       ef[0] = left ? p[2] : p[1]; ef[1] = left ? p[10] : p[7]; ef[2] = left ? p[8] : p[9];
       ef[3] = left ? p[18] : p[15]; ef[4] = left ? p[16] : p[17];
       if (active) {
-        if (!LIKE_R1 && BFLBM_G_MOMENT_SPACE) {  // moment space, in place: m <- (1 - w) m_old + v, then one inverse transform
+        if (!RATE1 && BFLBM_G_MOMENT_SPACE) {  // moment space, in place: m <- (1 - w) m_old + v, then one inverse transform
 #pragma unroll
           for (int a = 4; a < Q; ++a) mg[a] = So[(a - 4) * NT + tid];
         }
         if (!G_NORMALS_EARLY) mode_normals<NOISE, 1, TAB>(nk, ybg, Trig);
-        collide_species<NOISE, 1, RATE1, !LIKE_R1 && BFLBM_G_MOMENT_SPACE, FMA_NOISE>(P, ybg, C, mg);
+        collide_species<NOISE, 1, RATE1, !RATE1 && BFLBM_G_MOMENT_SPACE, FMA_NOISE>(P, ybg, C, mg);
       } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) mg[i] = 0.;
       }
       populations(mg, p);
-      if (REREAD && active) {
-        const double kg = keep_of(P, 1);
-        unsigned tok = 0;
-#pragma unroll
-        for (int i = 0; i < Q; ++i) {
-          p[i] = fma(kg, ld_off(XB.in[Q + i], pull_off(i) + tok), p[i]);
-          if (BFLBM_REREAD_CHUNK > 0 && (i + 1) % (BFLBM_REREAD_CHUNK > 0 ? BFLBM_REREAD_CHUNK : 1) == 0) tok = token(p[i]);
-        }
-      }
-      if (!LIKE_R1 && !BFLBM_G_MOMENT_SPACE && active) {
+      if (!RATE1 && !BFLBM_G_MOMENT_SPACE && active) {
         const double kg = keep_of(P, 1);
 #pragma unroll
         for (int i = 0; i < Q; ++i) p[i] = fma(kg, i < PARK_G ? So[i * NT + tid] : gk[i - PARK_G], p[i]);
