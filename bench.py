@@ -385,6 +385,7 @@ def run_b200(a):
                                    f"(BASELINE.json configs[{4 if a.scaling == 'weak' else 3}])",
                        "cells_per_gpu": cells_local, "algorithm": a.algo, "parallelism": f"z-slabs x{world}",
                        "l2": "working set (two lattices, %.1f GB per GPU) far exceeds the 126 MB L2; no flush needed" % (lat.device_bytes / 1e9),
+                       "timed_window_s": ms * 1e-3,  # a sustained run (>= 1 s) reaches the board power limit and runs ~3 % slower
                        "nonfinite_after_run": nan_count, "mass_rho": mass[0], "mass_phi": mass[1], "cells": cells,
                        "halo": None if world == 1 else ("peer-to-peer stores into CUDA-IPC-mapped mailboxes, device-side flags (no collective per step)"
                                                         if halo == "peer" else "NCCL send/recv (torch.distributed)"),
