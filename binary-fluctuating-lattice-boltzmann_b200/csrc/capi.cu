@@ -868,7 +868,13 @@ int ensure_buffer(bflbm_lattice* h, double** buf, size_t* have, size_t doubles) 
     *buf = nullptr;
     *have = 0;
   }
-  CU(cudaMalloc((void**)buf, doubles * sizeof(double)));
+  const cudaError_t e = cudaMalloc((void**)buf, doubles * sizeof(double));
+  if (e != cudaSuccess) {  // not sticky: clear it, so that the next launch check does not report it again; the lattice stays usable
+    cudaGetLastError();
+    *buf = nullptr;
+    return fail(BFLBM_ERR_CUDA, "asynchronous transfers: no room for %.2f GB of staging on the device (%s); the blocking calls need none",
+                (double)doubles * 8e-9, cudaGetErrorString(e));
+  }
   *have = doubles;
   h->bytes += doubles * sizeof(double);
   return 0;
